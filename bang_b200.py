@@ -1,0 +1,10 @@
+"""Import shim: exposes the package directory `bang-billion-scale-ann_b200/` as module `bang_b200`."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "bang-billion-scale-ann_b200")
+_spec = _u.spec_from_file_location("bang_b200", _os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["bang_b200"] = _mod
+_spec.loader.exec_module(_mod)
