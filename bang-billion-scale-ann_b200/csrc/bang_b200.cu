@@ -1,0 +1,608 @@
+// bang_b200.cu — C ABI (include/bang_b200.h) + host orchestration for the fused sm_100a search kernel.
+//
+// Mirrors the reference's BANGSearchInner<T> life cycle (BANG_Base/bang_search.cu:139-1068): load ->
+// set_searchparams -> alloc -> init -> query -> free -> unload.  Where the reference keeps the graph in
+// host RAM and crosses PCIe three times per hop (bang_search.cu:709,827-838), the whole index lives in
+// HBM here (optionally row-sharded over several GPUs) and one kernel launch runs the entire search.
+#include "bang_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "loader.h"
+#include "search_kernel.cuh"
+
+using namespace bang;
+
+static thread_local std::string g_err;
+extern "C" const char* bang_b200_last_error(void) { return g_err.c_str(); }
+
+static int set_err(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      return set_err(BANG_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                      std::to_string(__LINE__) + ")");                                   \
+  } while (0)
+
+struct bang_b200_ctx {
+  int dtype = BANG_DT_UINT8, mode = BANG_MODE_BASE, device = 0;
+  int shard = 0, n_shards = 1;
+  bool loaded = false, allocated = false;
+  // index
+  uint64_t N = 0, medoid = 0, entry_len = 0;
+  uint32_t D = 0, R = 0, n_chunks = 0;
+  uint32_t vec_bytes = 0, vec_units = 0, row_stride = 0, code_stride = 0;
+  uint64_t rows_local = 0;
+  uint8_t* d_rows = nullptr;
+  const uint8_t* rows[kMaxShards] = {nullptr};
+  void* imported[kMaxShards] = {nullptr};
+  uint8_t* d_codes = nullptr;
+  float* d_pivT = nullptr;
+  float* d_centroid = nullptr;
+  uint32_t* d_chunk_off = nullptr;
+  uint64_t device_bytes = 0;
+  // params
+  int k = 0, L = 0, distfn = BANG_DIST_L2, dists_layout = BANG_DISTS_RANK_MAJOR;
+  // per-alloc scratch
+  int Qcap = 0;
+  void* d_queries = nullptr;
+  uint64_t* d_ids = nullptr;
+  float* d_dists = nullptr;
+  uint32_t* d_bloom = nullptr;
+  uint32_t* d_counter = nullptr;
+  uint32_t *d_hops = nullptr, *d_sumdeg = nullptr, *d_npass = nullptr;
+  float* h_dists = nullptr;  // pinned staging for the layout transpose
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int grid = 0, ctas_per_sm = 0, sm_count = 0;
+  size_t smem = 0;
+  int lastQ = 0;
+  bang_b200_timing_t timing = {};
+};
+
+static size_t elem_size(int dtype) { return dtype == BANG_DT_FLOAT ? 4 : 1; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+typedef void (*search_fn_t)(const SearchArgs);
+typedef void (*table_fn_t)(const SearchArgs, float*);
+
+template <typename T>
+static search_fn_t pick_mode(int mode) {
+  switch (mode) {
+    case BANG_MODE_BASE: return bang_search_kernel<T, kBase>;
+    case BANG_MODE_INMEMORY: return bang_search_kernel<T, kInmemory>;
+    default: return bang_search_kernel<T, kExact>;
+  }
+}
+static search_fn_t pick_kernel(int dtype, int mode) {
+  switch (dtype) {
+    case BANG_DT_FLOAT: return pick_mode<float>(mode);
+    case BANG_DT_INT8: return pick_mode<int8_t>(mode);
+    default: return pick_mode<uint8_t>(mode);
+  }
+}
+static table_fn_t pick_table_kernel(int dtype) {
+  switch (dtype) {
+    case BANG_DT_FLOAT: return pq_table_kernel<float>;
+    case BANG_DT_INT8: return pq_table_kernel<int8_t>;
+    default: return pq_table_kernel<uint8_t>;
+  }
+}
+static size_t smem_for(const bang_b200_ctx* c, uint32_t L, uint32_t cand_cap) {
+  switch (c->dtype) {
+    case BANG_DT_FLOAT: return smem_bytes<float>(c->mode, c->n_chunks, c->vec_units, L, cand_cap);
+    case BANG_DT_INT8: return smem_bytes<int8_t>(c->mode, c->n_chunks, c->vec_units, L, cand_cap);
+    default: return smem_bytes<uint8_t>(c->mode, c->n_chunks, c->vec_units, L, cand_cap);
+  }
+}
+static uint32_t max_iter_for(int mode, int L) {
+  // bang_search.cu:53,603 (L+50) / BANG_Inmemory parANN.cu:30 (L+120) / BANG_Exactdistance parANN.cu:42 (4L+20)
+  return mode == BANG_MODE_BASE ? L + 50 : (mode == BANG_MODE_INMEMORY ? L + 120 : 4 * L + 20);
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+extern "C" int bang_b200_create(bang_handle_t* out, bang_dtype_t dtype, bang_mode_t mode, int device) {
+  if (!out) return set_err(BANG_E_ARG, "null handle pointer");
+  if (dtype < BANG_DT_INT8 || dtype > BANG_DT_FLOAT) return set_err(BANG_E_ARG, "bad dtype");
+  if (mode < BANG_MODE_BASE || mode > BANG_MODE_EXACTDISTANCE) return set_err(BANG_E_ARG, "bad mode");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return set_err(BANG_E_CUDA, "no CUDA device: the sm_100a kernels are the only search path");
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= ndev) return set_err(BANG_E_ARG, "device index out of range");
+  bang_b200_ctx* c = new bang_b200_ctx();
+  c->dtype = dtype;
+  c->mode = mode;
+  c->device = device;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  *out = c;
+  return BANG_OK;
+}
+
+extern "C" void bang_b200_destroy(bang_handle_t h) {
+  if (!h) return;
+  bang_b200_free(h);
+  bang_b200_unload(h);
+  delete h;
+}
+
+extern "C" int bang_b200_set_sharding(bang_handle_t h, int shard, int n_shards) {
+  if (!h) return set_err(BANG_E_ARG, "null handle");
+  if (h->loaded) return set_err(BANG_E_STATE, "set_sharding must precede load");
+  if (n_shards < 1 || n_shards > kMaxShards || shard < 0 || shard >= n_shards) return set_err(BANG_E_ARG, "bad shard spec");
+  h->shard = shard;
+  h->n_shards = n_shards;
+  return BANG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// load
+// ------------------------------------------------------------------------------------------------
+static int upload_pq(bang_b200_ctx* c, const PQHost& pq) {
+  const uint32_t D = c->D;
+  // transpose pivots to [D][256] as the reference does at load (bang_search.cu:281-285)
+  std::vector<float> pivT((size_t)D * 256);
+  for (uint32_t row = 0; row < 256; ++row)
+    for (uint32_t col = 0; col < D; ++col) pivT[(size_t)col * 256 + row] = pq.pivots[(size_t)row * D + col];
+  if (pq.chunk_off.size() != c->n_chunks + 1) return set_err(BANG_E_FORMAT, "chunk offsets count != n_chunks+1");
+  if (pq.chunk_off.back() != D) return set_err(BANG_E_FORMAT, "chunk offsets do not end at D");
+  for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
+    if (pq.chunk_off[i] > pq.chunk_off[i + 1]) return set_err(BANG_E_FORMAT, "chunk offsets not monotone");
+  CUDA_TRY(cudaMalloc(&c->d_pivT, pivT.size() * 4));
+  CUDA_TRY(cudaMalloc(&c->d_centroid, (size_t)D * 4));
+  CUDA_TRY(cudaMalloc(&c->d_chunk_off, pq.chunk_off.size() * 4));
+  CUDA_TRY(cudaMemcpy(c->d_pivT, pivT.data(), pivT.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_centroid, pq.centroid.data(), (size_t)D * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->d_chunk_off, pq.chunk_off.data(), pq.chunk_off.size() * 4, cudaMemcpyHostToDevice));
+  c->device_bytes += pivT.size() * 4 + (size_t)D * 4 + pq.chunk_off.size() * 4;
+  return BANG_OK;
+}
+
+// streams a file region through a pinned buffer to the device and runs `consume(d_chunk, first_item, n_items)`
+template <typename F>
+static int stream_file(const std::string& path, uint64_t offset, uint64_t item_bytes, uint64_t n_items, F consume) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return set_err(BANG_E_IO, "Could not open " + path);
+  if (fseeko(f, (off_t)offset, SEEK_SET) != 0) { fclose(f); return set_err(BANG_E_IO, "seek failed in " + path); }
+  const uint64_t budget = 64ull << 20;
+  const uint64_t per = std::max<uint64_t>(1, budget / item_bytes);
+  uint8_t* h_buf = nullptr;
+  uint8_t* d_buf = nullptr;
+  cudaError_t e = cudaMallocHost(&h_buf, per * item_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_buf, per * item_bytes);
+  int rc = BANG_OK;
+  if (e != cudaSuccess) rc = set_err(BANG_E_CUDA, std::string("staging alloc: ") + cudaGetErrorString(e));
+  for (uint64_t first = 0; rc == BANG_OK && first < n_items; first += per) {
+    const uint64_t n = std::min(per, n_items - first);
+    if (fread(h_buf, item_bytes, n, f) != n) { rc = set_err(BANG_E_FORMAT, "unexpected end of file in " + path); break; }
+    e = cudaMemcpy(d_buf, h_buf, n * item_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { rc = set_err(BANG_E_CUDA, std::string("H2D: ") + cudaGetErrorString(e)); break; }
+    rc = consume(d_buf, first, n);
+    if (rc == BANG_OK) {
+      e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) rc = set_err(BANG_E_CUDA, std::string("repack: ") + cudaGetErrorString(e));
+    }
+  }
+  if (h_buf) cudaFreeHost(h_buf);
+  if (d_buf) cudaFree(d_buf);
+  fclose(f);
+  return rc;
+}
+
+static int load_graph(bang_b200_ctx* c, const std::string& disk_path) {
+  uint64_t sz = 0;
+  if (!file_size(disk_path, &sz, &g_err)) return BANG_E_IO;
+  if (sz != c->N * c->entry_len)
+    return set_err(BANG_E_FORMAT, "Graph Index File size " + std::to_string(sz) + " != N*entry_len " +
+                                      std::to_string(c->N * c->entry_len));
+  c->vec_bytes = c->D * (uint32_t)elem_size(c->dtype);
+  c->vec_units = (c->vec_bytes + 15) / 16;
+  c->row_stride = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
+  c->rows_local = (c->N + c->n_shards - 1 - c->shard) / c->n_shards;
+  const size_t bytes = (size_t)c->rows_local * c->row_stride;
+  CUDA_TRY(cudaMalloc(&c->d_rows, std::max<size_t>(bytes, 256)));
+  c->device_bytes += bytes;
+  for (int s = 0; s < kMaxShards; ++s) c->rows[s] = nullptr;
+  c->rows[c->shard] = c->d_rows;
+  bang_b200_ctx* cc = c;
+  return stream_file(disk_path, 0, c->entry_len, c->N, [cc](uint8_t* d_chunk, uint64_t first, uint64_t n) -> int {
+    const uint64_t threads = n * 32;
+    repack_rows_kernel<<<(unsigned)((threads + 255) / 256), 256>>>(d_chunk, cc->entry_len, cc->vec_bytes, cc->R, cc->d_rows,
+                                                                   cc->row_stride, first, n, cc->shard, cc->n_shards);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? BANG_OK : set_err(BANG_E_CUDA, std::string("repack_rows: ") + cudaGetErrorString(e));
+  });
+}
+
+static int load_codes(bang_b200_ctx* c, const std::string& path) {
+  uint32_t n = 0, m = 0;
+  if (!read_bin_header(path, 1, &n, &m, &g_err)) return BANG_E_FORMAT;
+  if (n != c->N) return set_err(BANG_E_FORMAT, "PQ Compressed Vectors File holds " + std::to_string(n) + " points, graph has " + std::to_string(c->N));
+  if (m == 0) return set_err(BANG_E_FORMAT, "PQ Compressed Vectors File has 0 chunks");
+  c->n_chunks = m;
+  c->code_stride = (m + 31) / 32 * 32;
+  const size_t bytes = (size_t)c->N * c->code_stride;
+  CUDA_TRY(cudaMalloc(&c->d_codes, bytes));
+  c->device_bytes += bytes;
+  bang_b200_ctx* cc = c;
+  return stream_file(path, 8, m, c->N, [cc](uint8_t* d_chunk, uint64_t first, uint64_t nrows) -> int {
+    const uint64_t total = nrows * cc->code_stride;
+    repack_codes_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_chunk, cc->n_chunks,
+                                                                  cc->d_codes + first * cc->code_stride, cc->code_stride, nrows);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? BANG_OK : set_err(BANG_E_CUDA, std::string("repack_codes: ") + cudaGetErrorString(e));
+  });
+}
+
+static int check_common(bang_b200_ctx* c) {
+  if (c->R != (uint32_t)kMaxR) return set_err(BANG_E_UNSUPPORTED, "graph degree bound must be 64 (MAX_R, bang_search.cu:35,190)");
+  if (c->N == 0 || c->N > 0xFFFFFFFEull) return set_err(BANG_E_FORMAT, "bad dataset size");
+  if (c->medoid >= c->N) return set_err(BANG_E_FORMAT, "medoid out of range");
+  if (c->entry_len != (uint64_t)c->D * elem_size(c->dtype) + 4 + 4ull * c->R)
+    return set_err(BANG_E_FORMAT, "index entry length does not match D*sizeof(T)+4+4R (wrong element type?)");
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_unload(bang_handle_t h);
+
+static int finish_load(bang_b200_ctx* c, int rc) {
+  if (rc != BANG_OK) {
+    std::string keep = g_err;
+    c->loaded = true;  // let unload release partial allocations
+    bang_b200_unload(c);
+    g_err = keep;
+    return rc;
+  }
+  c->loaded = true;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_load(bang_handle_t c, const char* prefix_c) {
+  if (!c || !prefix_c) return set_err(BANG_E_ARG, "null argument");
+  if (c->loaded) return set_err(BANG_E_STATE, "index already loaded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const std::string prefix(prefix_c);
+  const std::string pivots = prefix + "_pq_pivots.bin", compressed = prefix + "_pq_compressed.bin";
+  const std::string disk = prefix + "_disk.bin", meta = prefix + "_disk_metadata.bin";
+  GraphMeta gm;
+  if (!read_graph_meta(meta, &gm, &g_err)) return BANG_E_IO;
+  c->N = gm.N; c->D = gm.D; c->R = gm.R; c->medoid = gm.medoid; c->entry_len = gm.entry_len;
+  c->device_bytes = 0;
+  int rc = check_common(c);
+  if (rc != BANG_OK) return rc;
+  if (c->mode != BANG_MODE_EXACTDISTANCE) {
+    rc = load_codes(c, compressed);
+    if (rc == BANG_OK) {
+      PQHost pq;
+      if (!read_pq_pivots_new(pivots, c->D, c->n_chunks, &pq, &g_err)) rc = BANG_E_IO;
+      else rc = upload_pq(c, pq);
+    }
+    if (rc != BANG_OK) return finish_load(c, rc);
+  }
+  return finish_load(c, load_graph(c, disk));
+}
+
+extern "C" int bang_b200_load_files(bang_handle_t c, const char* pq_pivots_bin, const char* pq_compressed_bin,
+                                    const char* disk_bin, const char* chunk_offsets_bin, const char* centroid_bin,
+                                    uint64_t N, uint32_t D, uint64_t medoid) {
+  if (!c || !disk_bin) return set_err(BANG_E_ARG, "null argument");
+  if (c->loaded) return set_err(BANG_E_STATE, "index already loaded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->N = N; c->D = D; c->R = kMaxR; c->medoid = medoid;
+  c->entry_len = (uint64_t)D * elem_size(c->dtype) + 4 + 4ull * kMaxR;
+  c->device_bytes = 0;
+  int rc = check_common(c);
+  if (rc != BANG_OK) return rc;
+  if (c->mode != BANG_MODE_EXACTDISTANCE) {
+    if (!pq_pivots_bin || !pq_compressed_bin || !chunk_offsets_bin || !centroid_bin)
+      return set_err(BANG_E_ARG, "PQ file names are required in Base/Inmemory mode");
+    rc = load_codes(c, pq_compressed_bin);
+    if (rc == BANG_OK) {
+      PQHost pq;
+      if (!read_pq_pivots_old(pq_pivots_bin, centroid_bin, chunk_offsets_bin, D, &pq, &g_err)) rc = BANG_E_IO;
+      else rc = upload_pq(c, pq);
+    }
+    if (rc != BANG_OK) return finish_load(c, rc);
+  }
+  return finish_load(c, load_graph(c, disk_bin));
+}
+
+extern "C" int bang_b200_unload(bang_handle_t c) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (!c->loaded) return BANG_OK;
+  cudaSetDevice(c->device);
+  for (int s = 0; s < kMaxShards; ++s)
+    if (c->imported[s]) { cudaIpcCloseMemHandle(c->imported[s]); c->imported[s] = nullptr; }
+  cudaFree(c->d_rows); cudaFree(c->d_codes); cudaFree(c->d_pivT); cudaFree(c->d_centroid); cudaFree(c->d_chunk_off);
+  c->d_rows = nullptr; c->d_codes = nullptr; c->d_pivT = nullptr; c->d_centroid = nullptr; c->d_chunk_off = nullptr;
+  c->loaded = false;
+  c->device_bytes = 0;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_export_shard(bang_handle_t c, void* out64) {
+  if (!c || !out64) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded) return set_err(BANG_E_STATE, "load first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  cudaIpcMemHandle_t hnd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hnd, c->d_rows));
+  memcpy(out64, &hnd, 64);
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_import_shard(bang_handle_t c, int shard, const void* in64) {
+  if (!c || !in64) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded) return set_err(BANG_E_STATE, "load first");
+  if (shard < 0 || shard >= c->n_shards || shard == c->shard) return set_err(BANG_E_ARG, "bad shard index");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t hnd;
+  memcpy(&hnd, in64, 64);
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+  c->imported[shard] = p;
+  c->rows[shard] = (const uint8_t*)p;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_info(bang_handle_t c, bang_b200_info_t* out) {
+  if (!c || !out) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded) return set_err(BANG_E_STATE, "no index loaded");
+  out->N = c->N; out->medoid = c->medoid; out->entry_len = c->entry_len;
+  out->D = c->D; out->R = c->R; out->n_chunks = c->n_chunks;
+  out->dtype = c->dtype; out->mode = c->mode; out->device_bytes = c->device_bytes;
+  return BANG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search params / alloc / init / free
+// ------------------------------------------------------------------------------------------------
+extern "C" int bang_b200_set_searchparams(bang_handle_t c, int recall, int worklist_length, bang_distfn_t dist) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (recall <= 0) return set_err(BANG_E_ARG, "recall (k) must be positive");
+  if (worklist_length < recall) return set_err(BANG_E_ARG, "WorkList Length must be at least recall_at");  // test_driver.cpp:394-398
+  if (worklist_length > BANG_B200_MAX_L) return set_err(BANG_E_ARG, "worklist_length exceeds MAX_L (512)");   // bang_search.cu:439
+  if (dist != BANG_DIST_L2 && dist != BANG_DIST_MIPS) return set_err(BANG_E_ARG, "bad distance function");
+  if (c->allocated) return set_err(BANG_E_STATE, "set_searchparams must precede alloc (bang_search.cu:370,379-384)");
+  c->k = recall;
+  c->L = worklist_length;
+  c->distfn = dist;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_set_dists_layout(bang_handle_t c, bang_dists_layout_t layout) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  c->dists_layout = layout;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (!c->loaded) return set_err(BANG_E_STATE, "bang_load must precede bang_alloc");
+  if (c->k <= 0 || c->L <= 0) return set_err(BANG_E_STATE, "bang_set_searchparams must precede bang_alloc");
+  if (c->allocated) return set_err(BANG_E_STATE, "already allocated; call bang_free first");
+  if (Q <= 0) return set_err(BANG_E_ARG, "numQueries must be positive");
+  for (int s = 0; s < c->n_shards; ++s)
+    if (!c->rows[s]) return set_err(BANG_E_STATE, "graph shard " + std::to_string(s) + " has not been imported");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint32_t max_iter = max_iter_for(c->mode, c->L);
+  c->smem = smem_for(c, c->L, max_iter + 1);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode);
+  int max_optin = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  if (c->smem > (size_t)max_optin)
+    return set_err(BANG_E_UNSUPPORTED, "PQ table (" + std::to_string(c->n_chunks) + " chunks) + worklist need " +
+                                           std::to_string(c->smem) + " B of shared memory, device allows " + std::to_string(max_optin));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, (const void*)fn, kThreads, c->smem));
+  if (c->ctas_per_sm < 1) return set_err(BANG_E_CUDA, "kernel does not fit on an SM");
+  c->grid = std::min(Q, c->ctas_per_sm * c->sm_count);
+  const size_t qbytes = (size_t)Q * c->D * elem_size(c->dtype);
+  CUDA_TRY(cudaMalloc(&c->d_queries, qbytes));
+  CUDA_TRY(cudaMalloc(&c->d_ids, (size_t)Q * c->k * sizeof(uint64_t)));
+  CUDA_TRY(cudaMalloc(&c->d_dists, (size_t)Q * c->k * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&c->d_bloom, (size_t)c->grid * kBloomWords * 4));
+  CUDA_TRY(cudaMalloc(&c->d_counter, 4));
+  CUDA_TRY(cudaMalloc(&c->d_hops, (size_t)Q * 4));
+  CUDA_TRY(cudaMalloc(&c->d_sumdeg, (size_t)Q * 4));
+  CUDA_TRY(cudaMalloc(&c->d_npass, (size_t)Q * 4));
+  CUDA_TRY(cudaMallocHost(&c->h_dists, (size_t)Q * c->k * sizeof(float)));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&c->ev0));
+  CUDA_TRY(cudaEventCreate(&c->ev1));
+  c->Qcap = Q;
+  c->allocated = true;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_init(bang_handle_t c, int Q) {
+  // The reference re-zeroes the bloom filters/worklists and re-seeds the medoid here (bang_search.cu:440-506).
+  // The fused kernel initialises all per-query state itself, so only the argument checks remain.
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (!c->allocated) return set_err(BANG_E_STATE, "bang_alloc must precede bang_init");
+  if (Q <= 0 || Q > c->Qcap) return set_err(BANG_E_ARG, "numQueries exceeds the allocated batch");
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_free(bang_handle_t c) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (!c->allocated) return BANG_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_queries); cudaFree(c->d_ids); cudaFree(c->d_dists); cudaFree(c->d_bloom); cudaFree(c->d_counter);
+  cudaFree(c->d_hops); cudaFree(c->d_sumdeg); cudaFree(c->d_npass);
+  cudaFreeHost(c->h_dists);
+  cudaStreamDestroy(c->stream);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  c->d_queries = nullptr; c->d_ids = nullptr; c->d_dists = nullptr; c->d_bloom = nullptr; c->d_counter = nullptr;
+  c->d_hops = c->d_sumdeg = c->d_npass = nullptr; c->h_dists = nullptr; c->stream = nullptr; c->ev0 = c->ev1 = nullptr;
+  c->allocated = false;
+  c->Qcap = 0;
+  return BANG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// query
+// ------------------------------------------------------------------------------------------------
+static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists) {
+  memset(a, 0, sizeof(*a));
+  for (int s = 0; s < kMaxShards; ++s) a->rows[s] = c->rows[s];
+  a->n_shards = c->n_shards;
+  a->row_stride = c->row_stride;
+  a->codes = c->d_codes;
+  a->code_stride = c->code_stride;
+  a->n_chunks = c->n_chunks;
+  a->pivT = c->d_pivT;
+  a->centroid = c->d_centroid;
+  a->chunk_off = c->d_chunk_off;
+  a->D = c->D;
+  a->vec_units = c->vec_units;
+  a->medoid = (uint32_t)c->medoid;
+  a->L = c->L;
+  a->k = c->k;
+  a->Q = Q;
+  a->q_dim = c->D - (c->distfn == BANG_DIST_MIPS ? 1 : 0);  // MIPS_EXTRA_DIM, bang.h:31; bang_search.cu:631
+  a->max_iter = max_iter_for(c->mode, c->L);
+  a->cand_cap = a->max_iter + 1;
+  a->queries = d_queries;
+  a->out_ids = d_ids;
+  a->out_dists = d_dists;
+  a->bloom = c->d_bloom;
+  a->counter = c->d_counter;
+  a->st_hops = c->d_hops;
+  a->st_sumdeg = c->d_sumdeg;
+  a->st_npass = c->d_npass;
+}
+
+static int launch_search(bang_b200_ctx* c, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists, cudaStream_t st) {
+  SearchArgs a;
+  fill_args(c, &a, d_queries, Q, d_ids, d_dists);
+  CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4, st));
+  const int grid = std::min(Q, c->grid);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode);
+  fn<<<grid, kThreads, c->smem, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  c->lastQ = Q;
+  c->timing.launches = 1;
+  c->timing.grid = grid;
+  c->timing.block = kThreads;
+  c->timing.smem_bytes = (uint32_t)c->smem;
+  c->timing.ctas_per_sm = c->ctas_per_sm;
+  return BANG_OK;
+}
+
+static int check_query_state(bang_b200_ctx* c, const void* q, int Q, const void* ids) {
+  if (!c || !q || !ids) return set_err(BANG_E_ARG, "null argument");
+  if (!c->allocated) return set_err(BANG_E_STATE, "bang_alloc/bang_init must precede bang_query");
+  if (Q <= 0 || Q > c->Qcap) return set_err(BANG_E_ARG, "num_queries exceeds the allocated batch");
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_query(bang_handle_t c, const void* queries, int Q, uint64_t* ids, float* dists) {
+  int rc = check_query_state(c, queries, Q, ids);
+  if (rc != BANG_OK) return rc;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint32_t q_dim = c->D - (c->distfn == BANG_DIST_MIPS ? 1 : 0);
+  const size_t qbytes = (size_t)Q * q_dim * elem_size(c->dtype);
+  CUDA_TRY(cudaMemcpyAsync(c->d_queries, queries, qbytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  rc = launch_search(c, c->d_queries, Q, c->d_ids, c->d_dists, c->stream);
+  if (rc != BANG_OK) return rc;
+  CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  const size_t n = (size_t)Q * c->k;
+  CUDA_TRY(cudaMemcpyAsync(ids, c->d_ids, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  uint64_t d2h = n * sizeof(uint64_t);
+  if (dists) {
+    float* dst = c->dists_layout == BANG_DISTS_QUERY_MAJOR ? dists : c->h_dists;
+    CUDA_TRY(cudaMemcpyAsync(dst, c->d_dists, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    d2h += n * sizeof(float);
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (dists && c->dists_layout == BANG_DISTS_RANK_MAJOR) {
+    // the reference hands back the first Q*k floats of its rank-major matrix (bang_search.cu:999,1297)
+    for (int q = 0; q < Q; ++q)
+      for (int j = 0; j < c->k; ++j) dists[(size_t)j * Q + q] = c->h_dists[(size_t)q * c->k + j];
+  }
+  CUDA_TRY(cudaEventElapsedTime(&c->timing.kernel_ms, c->ev0, c->ev1));
+  c->timing.h2d_bytes = qbytes;
+  c->timing.d2h_bytes = d2h;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_query_device(bang_handle_t c, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists,
+                                      void* cuda_stream) {
+  int rc = check_query_state(c, d_queries, Q, d_ids);
+  if (rc != BANG_OK) return rc;
+  if (!d_dists) return set_err(BANG_E_ARG, "null dists");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->timing.h2d_bytes = c->timing.d2h_bytes = 0;
+  c->timing.kernel_ms = 0.f;
+  return launch_search(c, d_queries, Q, d_ids, d_dists, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int bang_b200_last_stats(bang_handle_t c, uint32_t* hops, uint32_t* sum_deg, uint32_t* n_cand) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (!c->allocated || c->lastQ <= 0) return set_err(BANG_E_STATE, "no query has run");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t b = (size_t)c->lastQ * 4;
+  if (hops) CUDA_TRY(cudaMemcpy(hops, c->d_hops, b, cudaMemcpyDeviceToHost));
+  if (sum_deg) CUDA_TRY(cudaMemcpy(sum_deg, c->d_sumdeg, b, cudaMemcpyDeviceToHost));
+  if (n_cand) CUDA_TRY(cudaMemcpy(n_cand, c->d_npass, b, cudaMemcpyDeviceToHost));
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_last_timing(bang_handle_t c, bang_b200_timing_t* out) {
+  if (!c || !out) return set_err(BANG_E_ARG, "null argument");
+  *out = c->timing;
+  return BANG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1 on its own
+// ------------------------------------------------------------------------------------------------
+extern "C" int bang_b200_pq_table(bang_handle_t c, const void* queries, int Q, float* tables) {
+  if (!c || !queries || !tables) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded) return set_err(BANG_E_STATE, "no index loaded");
+  if (c->mode == BANG_MODE_EXACTDISTANCE) return set_err(BANG_E_UNSUPPORTED, "Exactdistance mode has no PQ table");
+  if (Q <= 0) return set_err(BANG_E_ARG, "numQueries must be positive");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint32_t q_dim = c->D - (c->distfn == BANG_DIST_MIPS ? 1 : 0);
+  const size_t qbytes = (size_t)Q * q_dim * elem_size(c->dtype);
+  const size_t tbytes = (size_t)Q * c->n_chunks * 256 * sizeof(float);
+  void* d_q = nullptr;
+  float* d_t = nullptr;
+  CUDA_TRY(cudaMalloc(&d_q, qbytes));
+  cudaError_t e = cudaMalloc(&d_t, tbytes);
+  if (e != cudaSuccess) { cudaFree(d_q); return set_err(BANG_E_CUDA, cudaGetErrorString(e)); }
+  SearchArgs a;
+  bang_b200_ctx tmp = *c;
+  tmp.L = tmp.L > 0 ? tmp.L : 1;
+  tmp.k = tmp.k > 0 ? tmp.k : 1;
+  fill_args(&tmp, &a, d_q, Q, nullptr, nullptr);
+  const size_t smem = (size_t)c->vec_units * 16 * (c->dtype == BANG_DT_FLOAT ? 1 : 4);
+  e = cudaMemcpy(d_q, queries, qbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    pick_table_kernel(c->dtype)<<<Q, kThreads, smem>>>(a, d_t);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(tables, d_t, tbytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_q);
+  cudaFree(d_t);
+  if (e != cudaSuccess) return set_err(BANG_E_CUDA, std::string("pq_table: ") + cudaGetErrorString(e));
+  return BANG_OK;
+}

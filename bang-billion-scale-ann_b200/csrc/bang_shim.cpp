@@ -1,0 +1,155 @@
+// bang_shim.cpp — `BANGSearch<T>` (include/bang.h) and the reference's C entry points over the C ABI.
+// Replaces the API shims of the reference (BANG_Base/bang_search.cu:70-135 and the `#if 0` block at
+// :1787-1806); each method is a one-line forward to bang_b200_*.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "bang.h"
+#include "bang_b200.h"
+
+namespace {
+
+template <typename T> struct dtype_of;
+template <> struct dtype_of<float> { static constexpr bang_dtype_t v = BANG_DT_FLOAT; };
+template <> struct dtype_of<uint8_t> { static constexpr bang_dtype_t v = BANG_DT_UINT8; };
+template <> struct dtype_of<int8_t> { static constexpr bang_dtype_t v = BANG_DT_INT8; };
+
+struct Impl {
+  bang_handle_t h = nullptr;
+  bang_dtype_t dtype;
+  bang_mode_t mode = BANG_MODE_BASE;
+  std::string err;
+};
+
+bang_mode_t mode_from_env() {
+  const char* m = getenv("BANG_B200_MODE");
+  if (!m) return BANG_MODE_BASE;
+  if (!strcmp(m, "inmemory")) return BANG_MODE_INMEMORY;
+  if (!strcmp(m, "exact") || !strcmp(m, "exactdistance")) return BANG_MODE_EXACTDISTANCE;
+  return BANG_MODE_BASE;
+}
+
+void note(Impl* p, int rc, const char* what) {
+  if (rc == BANG_OK) return;
+  p->err = std::string(what) + ": " + bang_b200_last_error();
+  fprintf(stderr, "bang_b200 error in %s\n", p->err.c_str());
+}
+
+}  // namespace
+
+template <typename T>
+BANGSearch<T>::BANGSearch() {
+  Impl* p = new Impl();
+  p->dtype = dtype_of<T>::v;
+  p->mode = mode_from_env();
+  m_pImpl = p;
+}
+
+template <typename T>
+BANGSearch<T>::~BANGSearch() {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  if (p->h) bang_b200_destroy(p->h);
+  delete p;
+}
+
+template <typename T>
+bool BANGSearch<T>::bang_set_mode(BangMode mode) {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  if (p->h) return false;
+  p->mode = static_cast<bang_mode_t>(mode);
+  return true;
+}
+
+template <typename T>
+bool BANGSearch<T>::bang_load(char* prefix) {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  if (!p->h) {
+    int rc = bang_b200_create(&p->h, p->dtype, p->mode, -1);
+    if (rc != BANG_OK) { note(p, rc, "bang_load"); p->h = nullptr; return false; }
+  }
+  int rc = bang_b200_load(p->h, prefix);
+  note(p, rc, "bang_load");
+  return rc == BANG_OK;
+}
+
+template <typename T>
+void BANGSearch<T>::bang_alloc(int numQueries) {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  note(p, p->h ? bang_b200_alloc(p->h, numQueries) : BANG_E_STATE, "bang_alloc");
+}
+
+template <typename T>
+void BANGSearch<T>::bang_init(int numQueries) {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  note(p, p->h ? bang_b200_init(p->h, numQueries) : BANG_E_STATE, "bang_init");
+}
+
+template <typename T>
+void BANGSearch<T>::bang_set_searchparams(int recall, int worklist_length, DistFunc nDistFunc) {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  note(p, p->h ? bang_b200_set_searchparams(p->h, recall, worklist_length, static_cast<bang_distfn_t>(nDistFunc)) : BANG_E_STATE,
+       "bang_set_searchparams");
+}
+
+template <typename T>
+void BANGSearch<T>::bang_query(T* query_array, int num_queries, result_ann_t* nearestNeighbours, float* nearestNeighbours_dist) {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  static_assert(sizeof(result_ann_t) == sizeof(uint64_t), "result_ann_t is 64-bit");
+  note(p, p->h ? bang_b200_query(p->h, query_array, num_queries, reinterpret_cast<uint64_t*>(nearestNeighbours), nearestNeighbours_dist)
+               : BANG_E_STATE,
+       "bang_query");
+}
+
+template <typename T>
+void BANGSearch<T>::bang_free() {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  if (p->h) note(p, bang_b200_free(p->h), "bang_free");
+}
+
+template <typename T>
+void BANGSearch<T>::bang_unload() {
+  Impl* p = static_cast<Impl*>(m_pImpl);
+  if (p->h) note(p, bang_b200_unload(p->h), "bang_unload");
+}
+
+template <typename T>
+const char* BANGSearch<T>::bang_last_error() const { return static_cast<Impl*>(m_pImpl)->err.c_str(); }
+
+template <typename T>
+void* BANGSearch<T>::bang_c_handle() const { return static_cast<Impl*>(m_pImpl)->h; }
+
+template class BANGSearch<float>;
+template class BANGSearch<uint8_t>;
+template class BANGSearch<int8_t>;
+
+// ---- the reference's C API (bang.h:89-101): one process-wide uint8 instance -------------------------
+static bang_handle_t g_c_handle = nullptr;
+
+extern "C" int bang_load_c(char* prefix) {
+  if (!g_c_handle) {
+    int rc = bang_b200_create(&g_c_handle, BANG_DT_UINT8, mode_from_env(), -1);
+    if (rc != BANG_OK) { g_c_handle = nullptr; return rc; }
+  }
+  return bang_b200_load(g_c_handle, prefix);
+}
+extern "C" void bang_set_searchparams_c(int recall, int worklist_length, int nDistFunc) {
+  if (g_c_handle) {
+    bang_b200_free(g_c_handle);  // parameters size the scratch; the next query re-allocates
+    bang_b200_set_searchparams(g_c_handle, recall, worklist_length, static_cast<bang_distfn_t>(nDistFunc));
+  }
+}
+extern "C" void bang_query_c(uint8_t* query_array, int num_queries, unsigned long* nearestNeighbours, float* nearestNeighbours_dist) {
+  if (!g_c_handle) return;
+  // the reference's C API has no alloc/init verbs: size the scratch on demand
+  bang_b200_free(g_c_handle);
+  if (bang_b200_alloc(g_c_handle, num_queries) != BANG_OK) return;
+  bang_b200_init(g_c_handle, num_queries);
+  bang_b200_query(g_c_handle, query_array, num_queries, reinterpret_cast<uint64_t*>(nearestNeighbours), nearestNeighbours_dist);
+}
+extern "C" void bang_unload_c(void) {
+  if (!g_c_handle) return;
+  bang_b200_destroy(g_c_handle);
+  g_c_handle = nullptr;
+}

@@ -1,0 +1,231 @@
+"""Parity of the sm_100a path against the oracle, through the C ABI (run with -m gpu on a B200).
+
+Bit-exact bar: ids identical and distances bit-identical to the oracle (ORDER_GPU) for every query,
+all three modes, all three element types; PQ tables bit-identical (tolerance stated by north_star is
+1e-5 relative — we hold 0).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bang_b200 import api, build, formats, recall
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MODE_O = {"base": O.MODE_BASE, "inmemory": O.MODE_INMEMORY, "exact": O.MODE_EXACT}
+
+
+def _search(fx, mode, k, L, queries=None):
+    s = api.BANGSearch(fx.dtype, mode)
+    assert s.bang_load(fx.prefix), getattr(s, "last_error", "")
+    s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+    s.bang_set_searchparams(k, L)
+    q = fx.queries if queries is None else queries
+    s.bang_alloc(len(q))
+    s.bang_init(len(q))
+    ids, dists = s.bang_query(q)
+    stats = s.last_stats(len(q))
+    timing = s.last_timing()
+    s.bang_free()
+    s.bang_unload()
+    return ids, dists, stats, timing
+
+
+@pytest.mark.parametrize("name", ["fx_u8", "fx_f32", "fx_i8"])
+def test_pq_table_bit_exact(fixtures, name):
+    fx = fixtures[name]
+    s = api.BANGSearch(fx.dtype, "base")
+    assert s.bang_load(fx.prefix)
+    got = s.pq_table(fx.queries)
+    ox = fx.oracle()
+    for i in range(len(fx.queries)):
+        want = ox.pq_table(fx.queries[i])
+        assert np.array_equal(got[i].view(np.uint32), want.view(np.uint32)), f"query {i}"
+    # and within 1e-5 relative of a float64 evaluation of the reference formula (bang_search.cu:1118-1129)
+    q = fx.queries[0].astype(np.float64) - fx.centroid.astype(np.float64)
+    ref = np.stack([((fx.pivots[:, a:b].astype(np.float64) - q[a:b]) ** 2).sum(1)
+                    for a, b in zip(fx.chunk_offsets[:-1], fx.chunk_offsets[1:])])
+    assert np.allclose(got[0], ref, rtol=1e-5, atol=1e-6)
+    s.bang_unload()
+
+
+@pytest.mark.parametrize("name", ["fx_u8", "fx_f32", "fx_i8"])
+@pytest.mark.parametrize("mode", ["base", "inmemory", "exact"])
+@pytest.mark.parametrize("L", [10, 32, 100])
+def test_search_bit_exact_vs_oracle(fixtures, name, mode, L):
+    fx = fixtures[name]
+    k = 10
+    ids, dists, stats, timing = _search(fx, mode, k, L)
+    ox = fx.oracle()
+    oids, odists, ost = ox.search(fx.queries, k, L, mode=MODE_O[mode], order=O.ORDER_GPU, stats=True)
+    assert timing.launches == 1 and timing.kernel_ms > 0
+    assert np.array_equal(ids, oids), f"{(ids != oids).any(1).sum()} of {len(ids)} queries differ"
+    assert np.array_equal(dists.view(np.uint32), odists.view(np.uint32))
+    assert np.array_equal(stats["hops"], ost["hops"])
+    assert np.array_equal(stats["sum_deg"], ost["sum_deg"])
+    assert np.array_equal(stats["n_cand"], ost["n_cand"])
+
+
+@pytest.mark.parametrize("name,mode,L,floor", [("fx_u8", "inmemory", 64, 95.0), ("fx_f32", "base", 64, 95.0),
+                                                 ("fx_u8", "exact", 32, 99.0)])
+def test_recall_vs_bruteforce(fixtures, name, mode, L, floor):
+    fx = fixtures[name]
+    ids, _, _, _ = _search(fx, mode, 10, L)
+    r = recall.calculate_recall(fx.gt_ids, fx.gt_dists, ids, 10)
+    assert r >= floor, r
+
+
+def test_dists_layout_rank_major_matches_reference_layout(fx_u8):
+    fx = fx_u8
+    s = api.BANGSearch(fx.dtype, "base")
+    assert s.bang_load(fx.prefix)
+    s.bang_set_searchparams(5, 20)
+    Q = 16
+    s.bang_alloc(Q)
+    s.bang_init(Q)
+    ids, d_rank = s.bang_query(fx.queries[:Q])  # default: rank-major, dists[j*Q+q] (bang_search.cu:999)
+    s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+    s.bang_init(Q)
+    ids2, d_q = s.bang_query(fx.queries[:Q])
+    assert np.array_equal(ids, ids2)
+    assert d_rank.shape == (5, Q) and d_q.shape == (Q, 5)
+    assert np.array_equal(d_rank.T, d_q)
+    assert (np.diff(d_q, axis=1) >= 0).all()  # ascending exact distance
+    s.bang_free()
+    s.bang_unload()
+
+
+def test_edge_cases(fx_u8):
+    fx = fx_u8
+    ox = fx.oracle()
+    # single query, k == L, k == 1
+    for k, L in [(1, 1), (10, 10), (3, 512)]:
+        ids, dists, _, _ = _search(fx, "base", k, L, fx.queries[:1])
+        oids, od = ox.search(fx.queries[:1], k, L, mode=O.MODE_BASE)
+        assert np.array_equal(ids, oids) and np.array_equal(dists, od)
+    # repeated init/query on one allocation gives identical results (init re-arms the search, bang_search.cu:440-506)
+    s = api.BANGSearch(fx.dtype, "inmemory")
+    assert s.bang_load(fx.prefix)
+    s.bang_set_searchparams(10, 40)
+    s.bang_alloc(len(fx.queries))
+    outs = []
+    for _ in range(3):
+        s.bang_init(len(fx.queries))
+        outs.append(s.bang_query(fx.queries)[0].copy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    # a ragged tail: fewer queries than allocated
+    s.bang_init(7)
+    ids7, _ = s.bang_query(fx.queries[:7])
+    assert np.array_equal(ids7, outs[0][:7])
+    s.bang_free()
+    s.bang_unload()
+
+
+def test_error_behaviour(fx_u8, tmp_path):
+    fx = fx_u8
+    s = api.BANGSearch(fx.dtype, "base")
+    assert not s.bang_load(str(tmp_path / "missing"))  # reference: bang_load returns false (bang_search.cu:152-177)
+    with pytest.raises(api.BangError):
+        s.bang_alloc(4)  # alloc before load
+    assert s.bang_load(fx.prefix)
+    with pytest.raises(api.BangError):
+        s.bang_alloc(4)  # alloc before set_searchparams (bang_search.cu:370,379-384)
+    with pytest.raises(api.BangError):
+        s.bang_set_searchparams(10, 5)  # L < k (test_driver.cpp:394-398)
+    with pytest.raises(api.BangError):
+        s.bang_set_searchparams(10, 513)  # > MAX_L (bang_search.cu:439)
+    s.bang_set_searchparams(10, 20)
+    with pytest.raises(api.BangError):
+        s.bang_query(fx.queries[:4])  # query before alloc
+    s.bang_alloc(4)
+    with pytest.raises(api.BangError):
+        s.bang_init(5)  # more queries than allocated
+    # wrong element type: entry length check
+    s2 = api.BANGSearch("float", "base")
+    assert not s2.bang_load(fx.prefix)
+    # truncated graph file
+    bad = str(tmp_path / "bad")
+    for suf in ("_pq_pivots.bin", "_pq_compressed.bin", "_disk_metadata.bin"):
+        with open(fx.prefix + suf, "rb") as f, open(bad + suf, "wb") as g:
+            g.write(f.read())
+    with open(fx.prefix + "_disk.bin", "rb") as f, open(bad + "_disk.bin", "wb") as g:
+        g.write(f.read()[:-100])
+    s3 = api.BANGSearch(fx.dtype, "base")
+    assert not s3.bang_load(bad)
+
+
+def test_load_files_old_layout_matches_prefix_load(fx_f32):
+    fx = fx_f32
+    ids_a, d_a, _, _ = _search(fx, "inmemory", 10, 48)
+    s = api.BANGSearch(fx.dtype, "inmemory")
+    p = fx.paths
+    assert s.bang_load_files(p.old_pivots, p.pq_compressed, p.disk, p.old_chunk_offsets, p.old_centroid, fx.N, fx.D, fx.medoid)
+    s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+    s.bang_set_searchparams(10, 48)
+    s.bang_alloc(len(fx.queries))
+    s.bang_init(len(fx.queries))
+    ids_b, d_b = s.bang_query(fx.queries)
+    assert np.array_equal(ids_a, ids_b) and np.array_equal(d_a, d_b)
+    # exact mode needs no PQ files at all
+    e = api.BANGSearch(fx.dtype, "exact")
+    assert e.bang_load_files(None, None, p.disk, None, None, fx.N, fx.D, fx.medoid)
+
+
+def test_mips_query_padding(fx_f32):
+    """ENUM_DIST_MIPS: queries carry D-1 dims and are padded with one zero dim in-kernel (bang_search.cu:1099-1113)."""
+    fx = fx_f32
+    q_short = np.ascontiguousarray(fx.queries[:, :-1])
+    q_pad = np.concatenate([q_short, np.zeros((len(q_short), 1), np.float32)], axis=1)
+    s = api.BANGSearch(fx.dtype, "base")
+    assert s.bang_load(fx.prefix)
+    s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+    s.bang_set_searchparams(10, 32, api.ENUM_DIST_MIPS)
+    s.bang_alloc(len(q_short))
+    s.bang_init(len(q_short))
+    ids, d = s.bang_query(q_short)
+    oids, od = fx.oracle().search(q_pad, 10, 32, mode=O.MODE_BASE)
+    assert np.array_equal(ids, oids) and np.array_equal(d, od)
+
+
+def test_cli_driver_reports_reference_table(fx_u8):
+    fx = fx_u8
+    exe = build.CLI
+    assert os.path.exists(exe)
+    env = dict(os.environ, BANG_B200_MODE="base")
+    out = subprocess.run([exe, fx.prefix, fx.paths.query, fx.paths.truth, str(len(fx.queries)), "10", "uint8", "l2", "40"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("40\t")]
+    assert len(lines) == 5  # five timed runs per L (test_driver.cpp:424)
+    ids, _, _, _ = _search(fx, "base", 10, 40)
+    want = recall.calculate_recall(fx.gt_ids, fx.gt_dists, ids, 10)
+    assert abs(float(lines[-1].split("\t")[3]) - want) < 0.01
+
+
+REF_DRIVER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_driver")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="oracle/_ref not built (reference not mounted at build time)")
+@pytest.mark.parametrize("name", ["fx_u8", "fx_f32"])
+def test_against_reference_cuda_build(fixtures, name, tmp_path):
+    """The UNMODIFIED reference (oracle/_ref/libbang.so) on this GPU vs the oracle vs the sm_100a path.
+    north_star: identical top-k ids on >= 99% of queries, recall within 0.1 pt."""
+    fx = fixtures[name]
+    k, L = 10, 48
+    out = str(tmp_path / "ref_ids.bin")
+    dt = {"uint8": "uint8", "int8": "int8", "float": "float"}[fx.dtype]
+    r = subprocess.run([REF_DRIVER, fx.prefix, fx.paths.query, str(len(fx.queries)), str(k), str(L), dt, out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ref_ids = np.fromfile(out, dtype=np.uint64).reshape(len(fx.queries), k)
+    ids, _, _, _ = _search(fx, "base", k, L)
+    same = (np.sort(ref_ids, 1) == np.sort(ids, 1)).all(1).mean()
+    r_ref = recall.calculate_recall(fx.gt_ids, fx.gt_dists, ref_ids, k)
+    r_new = recall.calculate_recall(fx.gt_ids, fx.gt_dists, ids, k)
+    print(f"{name}: identical top-k sets {same:.4f}; recall ref {r_ref:.2f} new {r_new:.2f}")
+    assert same >= 0.99
+    assert abs(r_ref - r_new) <= 0.1 + 1e-9
