@@ -64,7 +64,8 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
         raise RuntimeError("nvcc not found and libbang_b200.so not prebuilt")
     cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fopenmp,-O3",
            "-I", INCLUDE, "-I", CSRC, "-o", LIB_CUDA,
-           os.path.join(CSRC, "bang_b200.cu"), os.path.join(CSRC, "loader.cpp"), os.path.join(CSRC, "bang_shim.cpp"),
+           os.path.join(CSRC, "bang_b200.cu"), os.path.join(CSRC, "builder.cu"), os.path.join(CSRC, "loader.cpp"),
+           os.path.join(CSRC, "bang_shim.cpp"),
            "-lgomp"]
     if verbose_ptxas:
         cmd += ["-Xptxas", "-v"]

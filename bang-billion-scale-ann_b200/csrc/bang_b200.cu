@@ -19,6 +19,51 @@
 
 using namespace bang;
 
+namespace bang {
+// ------------------------------------------------------------------------------------------------
+// load-time repack kernels: file layouts -> HBM layouts
+// ------------------------------------------------------------------------------------------------
+// `_disk.bin` entry: [T vec[D]][u32 degree][u32 nbr[R]] (entry_len bytes, unaligned)  ->
+// HBM row: [u32 nbr[64], unused slots = kNoNbr][vec, zero padded to 16 B][pad to row_stride]
+__global__ void repack_rows_kernel(const uint8_t* __restrict__ src, uint64_t entry_len, uint32_t vec_bytes, uint32_t R,
+                                   uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t first_id, uint64_t n_ids,
+                                   uint32_t shard, uint32_t n_shards) {
+  // one warp per node
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= n_ids) return;
+  const uint64_t id = first_id + warp;
+  if (id % n_shards != shard) return;
+  const uint8_t* e = src + warp * entry_len;
+  uint8_t* d = dst + (id / n_shards) * (uint64_t)row_stride;
+  uint32_t deg = 0;
+  for (int b = 0; b < 4; ++b) deg |= (uint32_t)e[vec_bytes + b] << (8 * b);
+  if (deg > R) deg = R;
+  for (uint32_t i = lane; i < (uint32_t)kMaxR; i += 32) {
+    uint32_t v = kNoNbr;
+    if (i < deg) {
+      v = 0;
+      for (int b = 0; b < 4; ++b) v |= (uint32_t)e[vec_bytes + 4 + 4 * i + b] << (8 * b);
+    }
+    reinterpret_cast<uint32_t*>(d)[i] = v;
+  }
+  for (uint32_t i = lane; i < row_stride - kAdjBytes; i += 32) d[kAdjBytes + i] = i < vec_bytes ? e[i] : (uint8_t)0;
+}
+
+// PQ code row [m] -> permuted row [code_stride]: byte (32g + 4t + b) = chunk (32g + 8b + t)
+__global__ void repack_codes_kernel(const uint8_t* __restrict__ src, uint32_t m, uint8_t* __restrict__ dst,
+                                    uint32_t code_stride, uint64_t n_rows) {
+  const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t row = idx / code_stride;
+  const uint32_t p = (uint32_t)(idx % code_stride);
+  if (row >= n_rows) return;
+  const uint32_t g = p >> 5, t = (p & 31) >> 2, b = p & 3;
+  const uint32_t c = 32 * g + 8 * b + t;
+  dst[row * code_stride + p] = c < m ? src[row * m + c] : (uint8_t)0;
+}
+
+}  // namespace bang
+
 static thread_local std::string g_err;
 extern "C" const char* bang_b200_last_error(void) { return g_err.c_str(); }
 

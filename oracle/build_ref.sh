@@ -21,3 +21,12 @@ mkdir -p "$OUT"
 /usr/bin/g++ -O2 -std=c++14 -fopenmp -I"$REF" "$REF/test_driver.cpp" -o "$OUT/bang_search" \
     -L"$OUT" -lbang -L/usr/local/cuda/lib64 -lcudart -ldl -Wl,-rpath,'$ORIGIN' -Wl,-rpath,/usr/local/cuda/lib64
 echo "reference built into $OUT"
+# Drop-in proof: the reference's OWN driver source compiled against THIS repo's include/bang.h and linked
+# with libbang_b200.so instead of the reference library (no reference code in the link except the driver).
+ROOT="$(dirname "$HERE")"
+PKG="$ROOT/bang-billion-scale-ann_b200"
+if [ -f "$PKG/libbang_b200.so" ]; then
+  /usr/bin/g++ -O2 -std=c++14 -fopenmp -I"$ROOT/include" "$REF/test_driver.cpp" -o "$OUT/bang_search_dropin" \
+      -L"$PKG" -lbang_b200 -ldl -Wl,-rpath,'$ORIGIN/../../bang-billion-scale-ann_b200'
+  echo "drop-in driver built: $OUT/bang_search_dropin"
+fi
