@@ -2,11 +2,19 @@
 //
 // One CTA (128 threads) owns one query at a time and walks the whole greedy search for it without
 // leaving the SM: PQ table build (stage 1) -> { adjacency fetch, visited filter (stage 4a), PQ/exact
-// distances (stage 3), (dist,id) sort + worklist merge (stage 4b), parent selection (stage 2) }* ->
+// distances (stage 3), parent selection (stage 2), (dist,id) sort + worklist merge (stage 4b) }* ->
 // exact re-rank + top-k (stage 5).  CTAs are persistent: the grid is sized to the number of resident
 // CTAs and each CTA pulls query indices from a global counter.  What the reference does with ~5 kernel
 // launches, 2 memsets, up to 5 PCIe copies and 3 stream syncs per hop (bang_search.cu:701-958) is one
 // launch here; the LUT, worklist, candidate log and neighbour lists never leave shared memory.
+//
+// The search is a dependent pointer chase, so the kernel is organised around the per-hop critical path
+// (ncu: profiles/r1_*): each warp runs its own slice of the expansion (16 adjacency ids: hash, one L2
+// load per bloom word, fire-and-forget `red.or` to set, 8 lanes per accepted candidate for the
+// distance) with two CTA barriers per hop; the next node to expand is decided from the unsorted
+// distances BEFORE the sort/merge (it is the smaller of the best new candidate and the first unvisited
+// worklist entry — exactly what the merge would produce) and its adjacency row is requested at once, so
+// the merge overlaps the DRAM latency of the next hop.
 //
 // Semantics are the reference's with the deterministic choices documented in
 // oracle/bang_oracle.c; the oracle is bit-exact with this kernel (ORDER_GPU).
@@ -29,6 +37,7 @@ constexpr uint32_t kBloomWords = 12512u;  // ceil(399887/32)=12497, padded to a 
 constexpr uint32_t kNoNbr = 0xFFFFFFFFu;  // padding id in the HBM adjacency rows
 constexpr int kAdjBytes = kMaxR * 4;    // 256 B adjacency block at the head of each HBM row
 constexpr int kMaxShards = 8;
+#define BANG_B200_KERNEL_MAX_L 512  // MAX_L, bang.h:20
 
 enum Mode : int { kBase = 0, kInmemory = 1, kExact = 2 };
 
@@ -178,40 +187,46 @@ __device__ __forceinline__ float l2_row_8lane(const uint8_t* vec, const float* q
 // ------------------------------------------------------------------------------------------------
 // shared-memory state of one query
 // ------------------------------------------------------------------------------------------------
+constexpr int kWarps = kThreads / 32;         // 4
+constexpr int kIdsPerWarp = kMaxR / kWarps;   // 16 adjacency ids per warp (+ the medoid in warp 0 on the first hop)
+constexpr int kStage = 20;                    // per-warp staging slots for accepted ids (<= 17 used)
+constexpr int kWEnt = (BANG_B200_KERNEL_MAX_L + kThreads - 1) / kThreads;  // worklist entries per thread in a merge
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
 struct QState {
   float* q_f;        // [vec_units * E] query as fp32, zero padded
-  float* lut;        // [n_chunks][256]            (PQ modes)
-  float* w_d0;       // worklist, double buffered  [2][w_stride]
-  uint32_t* w_id0;
-  uint8_t* w_v0;
-  uint32_t w_stride;  // elements between the two buffers
-  __device__ __forceinline__ float* wd(uint32_t buf) const { return w_d0 + buf * w_stride; }
-  __device__ __forceinline__ uint32_t* wid(uint32_t buf) const { return w_id0 + buf * w_stride; }
-  __device__ __forceinline__ uint8_t* wv(uint32_t buf) const { return w_v0 + buf * w_stride; }
-  uint32_t* lst;     // [kListCap] raw candidate list (medoid +) adjacency
-  uint32_t* n_id;    // [kListCap] filtered, list order
-  float* n_d;
-  uint32_t* s_id;    // [kListCap] sorted by (dist, id)
-  float* s_d;
-  uint32_t* cand_id; // [cand_cap] expanded-node log
-  float* cand_d;     // exact distances of the log entries
-  uint32_t* scal;    // scalars, see below
+  float* lut;        // [n_chunks][256] (PQ modes); re-used for the candidates' exact distances in stage 5
+  float* w_d;        // worklist [w_cap], sorted by distance
+  uint32_t* w_id;
+  uint8_t* w_v;      // visited flags
+  uint32_t* n_id0;   // filtered neighbours, two buffers (hop parity) of kListCap
+  float* n_d0;
+  uint32_t* wstage;  // [kWarps][kStage]
+  uint32_t* cand_id; // [cand_cap] expanded-node log (PQ modes)
+  uint32_t* scal;
+  __device__ __forceinline__ uint32_t* n_id(uint32_t par) const { return n_id0 + par * kListCap; }
+  __device__ __forceinline__ float* n_d(uint32_t par) const { return n_d0 + par * kListCap; }
 };
-// scalar slots in QState::scal
-enum { S_NLIST = 0, S_NSIZE, S_WSIZE, S_CUR, S_PARENT, S_HAVE, S_NCAND, S_MARK, S_WMASK0, S_WMASK1, S_WMASK2, S_WMASK3,
-       S_QUERY, S_SUMDEG, S_NPASS, S_FOUND, S_COUNT };
+enum { S_CNT0 = 0, S_CNT1, S_QUERY, S_SUMDEG, S_NPASS, S_POS0, S_COUNT = 8 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline size_t lut_region_bytes(int mode, uint32_t n_chunks, uint32_t cand_cap) {
+  if (mode == kExact) return 0;
+  const size_t lut = (size_t)n_chunks * 256 * 4, cd = align_up((size_t)cand_cap * 4, 16);
+  return lut > cd ? lut : cd;
+}
 
 template <typename T>
 __host__ __device__ inline size_t smem_bytes(int mode, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap) {
   size_t b = 0;
   b += align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);
-  if (mode != kExact) b += (size_t)n_chunks * 256 * 4;
-  b += 2 * (align_up(L, 16) * 4 * 2 + align_up(L, 16));
-  b += (size_t)kListCap * 4 * 5;
-  b += align_up((size_t)cand_cap * 4, 16) * 2;
-  b += S_COUNT * 4 + 16;
+  b += lut_region_bytes(mode, n_chunks, cand_cap);
+  b += align_up(L, 16) * 9;                         // worklist: dist + id + visited
+  b += (size_t)kListCap * 4 * 2 * 2;                // neighbour lists, two parities
+  b += (size_t)kWarps * kStage * 4;
+  if (mode != kExact) b += align_up((size_t)cand_cap * 4, 16);
+  b += S_COUNT * 4;
   return align_up(b, 16);
 }
 
@@ -219,18 +234,15 @@ template <typename T>
 __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const SearchArgs& a) {
   size_t o = 0;
   s.q_f = (float*)(base + o); o += align_up((size_t)a.vec_units * Elem<T>::kPerUnit * 4, 16);
-  s.lut = (float*)(base + o); if (mode != kExact) o += (size_t)a.n_chunks * 256 * 4;
-  s.w_stride = (uint32_t)align_up(a.L, 16);
-  s.w_d0 = (float*)(base + o); o += (size_t)s.w_stride * 4 * 2;
-  s.w_id0 = (uint32_t*)(base + o); o += (size_t)s.w_stride * 4 * 2;
-  s.w_v0 = (uint8_t*)(base + o); o += (size_t)s.w_stride * 2;
-  s.lst = (uint32_t*)(base + o); o += kListCap * 4;
-  s.n_id = (uint32_t*)(base + o); o += kListCap * 4;
-  s.n_d = (float*)(base + o); o += kListCap * 4;
-  s.s_id = (uint32_t*)(base + o); o += kListCap * 4;
-  s.s_d = (float*)(base + o); o += kListCap * 4;
-  s.cand_id = (uint32_t*)(base + o); o += align_up((size_t)a.cand_cap * 4, 16);
-  s.cand_d = (float*)(base + o); o += align_up((size_t)a.cand_cap * 4, 16);
+  s.lut = (float*)(base + o); o += lut_region_bytes(mode, a.n_chunks, a.cand_cap);
+  const size_t wcap = align_up(a.L, 16);
+  s.w_d = (float*)(base + o); o += wcap * 4;
+  s.w_id = (uint32_t*)(base + o); o += wcap * 4;
+  s.w_v = (uint8_t*)(base + o); o += wcap;
+  s.n_id0 = (uint32_t*)(base + o); o += (size_t)kListCap * 4 * 2;
+  s.n_d0 = (float*)(base + o); o += (size_t)kListCap * 4 * 2;
+  s.wstage = (uint32_t*)(base + o); o += (size_t)kWarps * kStage * 4;
+  s.cand_id = (uint32_t*)(base + o); if (mode != kExact) o += align_up((size_t)a.cand_cap * 4, 16);
   s.scal = (uint32_t*)(base + o);
 }
 
@@ -263,86 +275,85 @@ __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, floa
   for (uint32_t i = threadIdx.x; i < n; i += kThreads) q_f[i] = i < a.q_dim ? (float)src[i] : 0.0f;
 }
 
-// ------------------------------------------------------------------------------------------------
-// stage 4a: visited filter (bloom filter in L2-resident global memory, one region per resident CTA).
-// Sequential-in-list-order semantics: each accepted id's bits are visible to the ids after it.
-// Executed by warp 0; rounds of 32 ids.  Fast path: test, atomicOr, and detect through the atomics'
-// return values whether two lanes of the round touched the same bit; only then (rare) the accept
-// decisions are re-derived sequentially (the final bit state is the union either way).
-// ------------------------------------------------------------------------------------------------
-template <int MODE>
-__device__ __forceinline__ void filter_list(const QState& s, uint32_t* bloom, uint32_t n_list) {
-  const uint32_t lane = threadIdx.x & 31;
-  uint32_t n_out = 0;
-  for (uint32_t base = 0; base < n_list; base += 32) {
-    const uint32_t i = base + lane;
-    const bool valid = i < n_list;
-    const uint32_t id = valid ? s.lst[i] : 0u;
-    const uint32_t p1 = hash1(id);
-    const uint32_t p2 = (MODE == kExact) ? p1 : hash2(id);
-    const uint32_t w1 = p1 >> 5, b1 = 1u << (p1 & 31), w2 = p2 >> 5, b2 = 1u << (p2 & 31);
-    bool s1 = false, s2 = false;
-    if (valid) {
-      s1 = (__ldcg(bloom + w1) & b1) != 0;
-      s2 = (MODE == kExact) ? s1 : ((__ldcg(bloom + w2) & b2) != 0);
-    }
-    bool accept = valid && !(s1 && s2);
-    bool conflict = false;
-    __syncwarp();  // every lane's test precedes every lane's set
-    if (accept) {
-      const uint32_t o1 = atomicOr(bloom + w1, b1);
-      conflict = ((o1 & b1) != 0) && !s1;
-      if (MODE != kExact && p2 != p1) {
-        const uint32_t o2 = atomicOr(bloom + w2, b2);
-        conflict = conflict || (((o2 & b2) != 0) && !s2);
-      }
-    }
-    const uint32_t amask = __ballot_sync(0xffffffffu, accept);
-    if (__any_sync(0xffffffffu, conflict)) {
-      // re-derive accept decisions in list order
-      uint32_t todo = amask;
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const bool acc_src = __shfl_sync(0xffffffffu, (int)(!(s1 && s2)), src) != 0;
-        const uint32_t q1 = __shfl_sync(0xffffffffu, p1, src);
-        const uint32_t q2 = __shfl_sync(0xffffffffu, p2, src);
-        if (acc_src && (int)lane > src) {
-          s1 = s1 || p1 == q1 || p1 == q2;
-          s2 = s2 || p2 == q1 || p2 == q2;
-        }
-      }
-      accept = valid && ((amask >> lane) & 1u) && !(s1 && s2);
-    }
-    const uint32_t fmask = __ballot_sync(0xffffffffu, accept);
-    if (accept) s.n_id[n_out + __popc(fmask & ((1u << lane) - 1u))] = id;
-    n_out += __popc(fmask);
-  }
-  if (lane == 0) s.scal[S_NSIZE] = n_out;
+// adjacency prefetch: lanes 0..15 of warp w request ids [16w, 16w+16) of `node`'s HBM row
+__device__ __forceinline__ uint32_t fetch_adj(const SearchArgs& a, uint32_t node) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t v = kNoNbr;
+  if (lane < (uint32_t)kIdsPerWarp) v = ld_nc_u32(row_ptr(a, node) + 4 * (kIdsPerWarp * warp + lane));
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 3 (PQ): dist[i] = sum_c lut[c][code[id_i][c]] — 8 lanes per candidate; lane t owns chunks
-// t, t+8, ... ascending (the reference's split), partials combined by the 8-lane tree.  The HBM code
-// rows are permuted at load so that lane t's chunks 32g+t, 32g+8+t, 32g+16+t, 32g+24+t are one aligned
-// 32-bit word: one 32-byte sector per candidate per 32 chunks, fully used.
+// expansion of one node = stages 4a + 3.  Every warp owns 16 adjacency ids (already requested by
+// fetch_adj): visited filter with snapshot semantics (all tests of a list precede all insertions — one
+// barrier), then 8 lanes per accepted candidate for the PQ / exact distance.  Accepted (id, dist) pairs
+// land unordered in the neighbour buffer of this hop's parity; returns their count.
+//   filter   neighbor_filtering_new + hashFn1_d/2_d   bang_search.cu:1140-1189 (Exact: hash 1 only)
+//   PQ dist  compute_neighborDist_par                 bang_search.cu:1201-1241: lane t owns chunks t, t+8, ...
+//            ascending, partials combined by the 8-lane tree.  The HBM code rows are permuted at load so
+//            lane t's chunks 32g+t, 32g+8+t, 32g+16+t, 32g+24+t are one aligned 32-bit word: one 32-byte
+//            sector per candidate per 32 chunks, fully used.
+//   exact    compute_neighborDist_par                 BANG_Exactdistance/parANN.cu:1139-1179
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pq_distances(const SearchArgs& a, const QState& s, uint32_t n) {
-  const uint32_t tid = threadIdx.x, t = tid & 7, slot = tid >> 3;  // 16 candidates per pass
-  const uint32_t groups = (a.n_chunks + 31) >> 5;
-  constexpr int kPass = (kListCap + 15) / 16;  // 5
-  if (groups == 1) {
-    uint32_t w[kPass];
+template <typename T, int MODE>
+__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint32_t* bloom, uint32_t my_nb, bool first,
+                                           uint32_t par) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t id = kNoNbr;
+  if (lane < (uint32_t)kIdsPerWarp) id = my_nb;
+  else if (first && warp == 0 && lane == (uint32_t)kIdsPerWarp) id = a.medoid;  // [medoid] ++ adj(medoid) on the first hop
+  const bool valid = id != kNoNbr;
+  uint32_t w1 = 0, b1 = 0, w2 = 0, b2 = 0;
+  bool acc = false;
+  if (valid) {
+    const uint32_t p1 = hash1(id);
+    w1 = p1 >> 5; b1 = 1u << (p1 & 31);
+    if (MODE == kExact) {
+      acc = (__ldcg(bloom + w1) & b1) == 0;
+    } else {
+      const uint32_t p2 = hash2(id);
+      w2 = p2 >> 5; b2 = 1u << (p2 & 31);
+      const uint32_t x1 = __ldcg(bloom + w1), x2 = __ldcg(bloom + w2);
+      acc = !((x1 & b1) && (x2 & b2));
+    }
+  }
+  // all tests of this list are done before any insertion (also counts the degree for the statistics)
+  const uint32_t deg = __syncthreads_count(valid && lane < (uint32_t)kIdsPerWarp);
+  if (acc) {  // results unused -> RED.OR, nothing waits on them
+    atomicOr(bloom + w1, b1);
+    if (MODE != kExact) atomicOr(bloom + w2, b2);
+  }
+  const uint32_t amask = __ballot_sync(0xffffffffu, acc);
+  const uint32_t cnt = __popc(amask);
+  uint32_t base = 0;
+  if (lane == 0 && cnt) base = atomicAdd(&s.scal[S_CNT0 + par], cnt);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  uint32_t* stage = s.wstage + warp * kStage;
+  if (acc) stage[__popc(amask & ((1u << lane) - 1u))] = id;
+  __syncwarp();
+  uint32_t* n_id = s.n_id(par);
+  float* n_d = s.n_d(par);
+  const uint32_t t = lane & 7, g = lane >> 3;  // 4 candidates per warp pass
+  constexpr int kPass = (kIdsPerWarp + 1 + 3) / 4;  // 5
+  if (MODE == kExact) {
+    for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
+      const uint32_t k = k0 + g;
+      const uint32_t cid = k < cnt ? stage[k] : a.medoid;
+      const float d = l2_row_8lane<T>(row_ptr(a, cid) + kAdjBytes, s.q_f, a.vec_units, t);
+      if (t == 0 && k < cnt) { n_id[base + k] = cid; n_d[base + k] = d; }
+    }
+  } else if (a.n_chunks <= 32) {
+    uint32_t w[kPass], cid[kPass];
 #pragma unroll
     for (int p = 0; p < kPass; ++p) {
-      const uint32_t i = p * 16 + slot;
-      w[p] = 0;
-      if (i < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[i] * a.code_stride + 4 * t);
+      const uint32_t k = p * 4 + g;
+      w[p] = 0; cid[p] = 0;
+      if (k < cnt) { cid[p] = stage[k]; w[p] = ld_nc_u32(a.codes + (size_t)cid[p] * a.code_stride + 4 * t); }
     }
 #pragma unroll
     for (int p = 0; p < kPass; ++p) {
-      const uint32_t i = p * 16 + slot;
-      if (p * 16 < (int)n) {  // uniform per pass
+      if (p * 4 < (int)cnt) {  // warp-uniform
+        const uint32_t k = p * 4 + g;
         float sum = 0.0f;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
@@ -350,187 +361,187 @@ __device__ __forceinline__ void pq_distances(const SearchArgs& a, const QState& 
           if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((w[p] >> (8 * b)) & 0xff)]);
         }
         sum = tree8(sum);
-        if (t == 0 && i < n) s.n_d[i] = sum;
+        if (t == 0 && k < cnt) { n_id[base + k] = cid[p]; n_d[base + k] = sum; }
       }
     }
   } else {
-    for (uint32_t p0 = 0; p0 < n; p0 += 16) {
-      const uint32_t i = p0 + slot;
+    const uint32_t groups = (a.n_chunks + 31) >> 5;
+    for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
+      const uint32_t k = k0 + g;
+      const uint32_t cid = k < cnt ? stage[k] : 0u;
+      const uint8_t* row = a.codes + (size_t)cid * a.code_stride + 4 * t;
       float sum = 0.0f;
-      const uint8_t* row = a.codes + (size_t)(i < n ? s.n_id[i] : 0u) * a.code_stride + 4 * t;
-      for (uint32_t g = 0; g < groups; g += 2) {
-        const uint32_t wa = (i < n) ? ld_nc_u32(row + g * 32) : 0u;
-        const uint32_t wb = (i < n && g + 1 < groups) ? ld_nc_u32(row + (g + 1) * 32) : 0u;
+      for (uint32_t gg = 0; gg < groups; gg += 2) {
+        const uint32_t wa = ld_nc_u32(row + gg * 32);
+        const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32) : 0u;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const uint32_t c = g * 32 + t + 8 * b;
+          const uint32_t c = gg * 32 + t + 8 * b;
           if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((wa >> (8 * b)) & 0xff)]);
         }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const uint32_t c = (g + 1) * 32 + t + 8 * b;
+          const uint32_t c = (gg + 1) * 32 + t + 8 * b;
           if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((wb >> (8 * b)) & 0xff)]);
         }
       }
       sum = tree8(sum);
-      if (t == 0 && i < n) s.n_d[i] = sum;
+      if (t == 0 && k < cnt) { n_id[base + k] = cid; n_d[base + k] = sum; }
     }
   }
-}
-
-// stage 3 (exact): full-precision rows, 8 lanes per candidate, whole 128-byte lines per request
-template <typename T>
-__device__ __forceinline__ void exact_distances(const SearchArgs& a, const QState& s, uint32_t n) {
-  const uint32_t tid = threadIdx.x, t = tid & 7, slot = tid >> 3;
-  for (uint32_t p0 = 0; p0 < n; p0 += 16) {
-    const uint32_t i = p0 + slot;
-    const uint32_t id = i < n ? s.n_id[i] : a.medoid;
-    const float d = l2_row_8lane<T>(row_ptr(a, id) + kAdjBytes, s.q_f, a.vec_units, t);
-    if (t == 0 && i < n) s.n_d[i] = d;
+  __syncthreads();
+  const uint32_t n = s.scal[S_CNT0 + par];
+  if (tid == 0) {
+    s.scal[S_CNT0 + (par ^ 1u)] = 0;  // next hop's counter; its last readers passed the barrier above
+    s.scal[S_SUMDEG] += deg;
+    s.scal[S_NPASS] += n;
   }
+  return n;
 }
 
-// rank sort of the (<= 65) filtered neighbours by (dist, id) -> s_id / s_d
-__device__ __forceinline__ void sort_neighbours(const QState& s, uint32_t n) {
+// (dist, id)-minimum of the unsorted neighbour list, the number of entries closer than `maxd`, and the
+// medoid's distance if it is in the list.  Every warp computes the same values redundantly from shared
+// memory, so no barrier is needed to publish the decision that follows.
+struct Best { float d; uint32_t id; uint32_t below; float med_d; bool med_in; };
+__device__ __forceinline__ Best scan_neighbours(const QState& s, uint32_t par, uint32_t n, uint32_t medoid, bool skip_medoid,
+                                                float maxd) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t* n_id = s.n_id(par);
+  const float* n_d = s.n_d(par);
+  Best b{3.402823466e+38f, kNone, 0u, 0.0f, false};
+  for (uint32_t i = lane; i < n; i += 32) {
+    const float d = n_d[i];
+    const uint32_t id = n_id[i];
+    b.below += d < maxd ? 1u : 0u;
+    if (id == medoid) { b.med_in = true; b.med_d = d; if (skip_medoid) continue; }
+    if (key_less(d, id, b.d, b.id)) { b.d = d; b.id = id; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, b.d, off);
+    const uint32_t oid = __shfl_xor_sync(0xffffffffu, b.id, off);
+    if (key_less(od, oid, b.d, b.id)) { b.d = od; b.id = oid; }
+    b.below += __shfl_xor_sync(0xffffffffu, b.below, off);
+    const float omd = __shfl_xor_sync(0xffffffffu, b.med_d, off);
+    const bool omi = __shfl_xor_sync(0xffffffffu, (int)b.med_in, off) != 0;
+    if (omi) { b.med_in = true; b.med_d = omd; }
+  }
+  return b;
+}
+
+// first unvisited worklist entry at or after `start` (warp-redundant, shared memory only)
+__device__ __forceinline__ uint32_t scan_unvisited(const QState& s, uint32_t start, uint32_t ws) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t b0 = start; b0 < ws; b0 += 32) {
+    const uint32_t j = b0 + lane;
+    const uint32_t m = __ballot_sync(0xffffffffu, j < ws && s.w_v[j] == 0);
+    if (m) return b0 + (uint32_t)__ffs(m) - 1u;
+  }
+  return kNone;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 4b: (dist, id) sort of the new neighbours + merge into the worklist, in place.
+// compute_BestLSets_par_sort_msort + compute_BestLSets_par_merge (bang_search.cu:1533-1585, 1605-1715):
+// only the `nb` closest new entries take part (nb as the reference computes nbrsBound); a new entry
+// goes before old entries of equal distance; the list is truncated to L.  New entries are unvisited,
+// except `flag_id` (the node just chosen for expansion / the reference's d_mark) and, in the first
+// merge, the medoid.  Returns the new size; scal[S_POS0] = position of the closest new entry.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QState& s, uint32_t par, uint32_t n, uint32_t nb,
+                                                   uint32_t ws, bool first, uint32_t flag_id) {
   const uint32_t tid = threadIdx.x;
+  uint32_t* s_id = s.n_id(par ^ 1u);  // the other parity's buffer is idle until the next hop's expansion
+  float* s_d = s.n_d(par ^ 1u);
+  const uint32_t* n_id = s.n_id(par);
+  const float* n_d = s.n_d(par);
   if (tid < n) {
-    const float d = s.n_d[tid];
-    const uint32_t id = s.n_id[tid];
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; ++j) rank += key_less(s.n_d[j], s.n_id[j], d, id) ? 1u : 0u;
-    s.s_d[rank] = d;
-    s.s_id[rank] = id;
+    const float d = n_d[tid];
+    const uint32_t id = n_id[tid];
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < n; ++j) r += key_less(n_d[j], n_id[j], d, id) ? 1u : 0u;
+    if (r < nb) { s_d[r] = d; s_id[r] = id; }
   }
-}
-
-// stage 4b: merge the sorted neighbours into the worklist (compute_BestLSets_par_merge,
-// bang_search.cu:1636-1709).  Block-uniform control flow; returns with W in buffer s.scal[S_CUR].
-__device__ __forceinline__ void merge_worklist(const SearchArgs& a, const QState& s, uint32_t n, bool first) {
-  const uint32_t tid = threadIdx.x;
-  const uint32_t L = a.L;
-  if (n == 0) return;  // uniform
-  uint32_t cur = s.scal[S_CUR];
-  if (first) {
-    const uint32_t nb = min(n, L);
-    for (uint32_t i = tid; i < nb; i += kThreads) {
-      s.wid(cur)[i] = s.s_id[i];
-      s.wd(cur)[i] = s.s_d[i];
-      s.wv(cur)[i] = (s.s_id[i] == a.medoid) ? 1 : 0;
+  __syncthreads();
+  if (first) {  // iter == 1 branch (:1636-1646): the worklist is the head of the sorted list
+    if (tid < nb) {
+      const uint32_t id = s_id[tid];
+      s.w_d[tid] = s_d[tid];
+      s.w_id[tid] = id;
+      s.w_v[tid] = (id == a.medoid || id == flag_id) ? 1 : 0;
     }
+    if (tid == 0) s.scal[S_POS0] = 0;
     __syncthreads();
-    if (tid == 0) s.scal[S_WSIZE] = nb;
-    __syncthreads();
-    return;
+    return nb;
   }
-  const uint32_t ws = s.scal[S_WSIZE];
-  const float maxd = s.wd(cur)[ws - 1];
-  const uint32_t lim = min(L, n);
-  // sorted ascending => the leading run with d < maxd is exactly the set with d < maxd
-  uint32_t nb = __syncthreads_count(tid < lim && s.s_d[tid] < maxd);
-  nb = max(nb, min(L - ws, n));
-  if (nb == 0) return;  // uniform
-  const uint32_t newsize = min(ws + nb, L);
-  const uint32_t nxt = cur ^ 1u;
-  if (tid < nb) {  // new entry: position = lower_bound(W, d) + index  (new before old on ties)
-    const float d = s.s_d[tid];
+  const uint32_t newsize = min(ws + nb, a.L);
+  float od[kWEnt];
+  uint32_t oid[kWEnt], opos[kWEnt];
+  uint8_t ov[kWEnt];
+#pragma unroll
+  for (int e = 0; e < kWEnt; ++e) {  // old entry: position = index + upper_bound(new, d)
+    const uint32_t j = tid + e * kThreads;
+    opos[e] = kNone;
+    if (j < ws) {
+      od[e] = s.w_d[j]; oid[e] = s.w_id[j]; ov[e] = s.w_v[j];
+      uint32_t lo = 0, hi = nb;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (od[e] >= s_d[mid]) lo = mid + 1; else hi = mid;
+      }
+      opos[e] = j + lo;
+    }
+  }
+  uint32_t npos = kNone, nid = 0;
+  float nd = 0.0f;
+  if (tid < nb) {  // new entry: position = index + lower_bound(W, d)  (new before old on ties)
+    nd = s_d[tid]; nid = s_id[tid];
     uint32_t lo = 0, hi = ws;
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
-      if (d <= s.wd(cur)[mid]) hi = mid; else lo = mid + 1;
+      if (nd <= s.w_d[mid]) hi = mid; else lo = mid + 1;
     }
-    const uint32_t pos = lo + tid;
-    if (pos < newsize) {
-      s.wd(nxt)[pos] = d;
-      s.wid(nxt)[pos] = s.s_id[tid];
-      s.wv(nxt)[pos] = 0;
-    }
-  }
-  for (uint32_t j = tid; j < ws; j += kThreads) {  // old entry: position = upper_bound(new, d) + index
-    const float d = s.wd(cur)[j];
-    uint32_t lo = 0, hi = nb;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (d >= s.s_d[mid]) lo = mid + 1; else hi = mid;
-    }
-    const uint32_t pos = lo + j;
-    if (pos < newsize) {
-      s.wd(nxt)[pos] = d;
-      s.wid(nxt)[pos] = s.wid(cur)[j];
-      s.wv(nxt)[pos] = s.wv(cur)[j];
-    }
+    npos = lo + tid;
+    if (tid == 0) s.scal[S_POS0] = npos;
   }
   __syncthreads();
-  if (tid == 0) { s.scal[S_WSIZE] = newsize; s.scal[S_CUR] = nxt; }
-  __syncthreads();
-}
-
-// index of the first unvisited worklist entry, or 0xFFFFFFFF (all threads get the value)
-__device__ __forceinline__ uint32_t first_unvisited(const QState& s) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t ws = s.scal[S_WSIZE], cur = s.scal[S_CUR];
-  for (uint32_t base = 0; base < ws; base += kThreads) {
-    const uint32_t j = base + tid;
-    const bool un = j < ws && s.wv(cur)[j] == 0;
-    const uint32_t m = __ballot_sync(0xffffffffu, un);
-    if (lane == 0) s.scal[S_WMASK0 + warp] = m;
-    __syncthreads();
-    uint32_t found = 0xFFFFFFFFu;
 #pragma unroll
-    for (int w = kThreads / 32 - 1; w >= 0; --w) {
-      const uint32_t mw = s.scal[S_WMASK0 + w];
-      if (mw) found = base + w * 32 + (__ffs(mw) - 1);
-    }
-    __syncthreads();
-    if (found != 0xFFFFFFFFu) return found;
-  }
-  return 0xFFFFFFFFu;
+  for (int e = 0; e < kWEnt; ++e)
+    if (opos[e] < newsize) { s.w_d[opos[e]] = od[e]; s.w_id[opos[e]] = oid[e]; s.w_v[opos[e]] = ov[e]; }
+  if (npos < newsize) { s.w_d[npos] = nd; s.w_id[npos] = nid; s.w_v[npos] = (nid == flag_id) ? 1 : 0; }
+  __syncthreads();
+  return newsize;
+}
+
+// number of new entries the reference's merge admits (nbrsBound, bang_search.cu:1651-1656)
+__device__ __forceinline__ uint32_t admit_count(uint32_t below, uint32_t n, uint32_t ws, uint32_t L) {
+  return max(min(below, min(L, n)), min(L - ws, n));
 }
 
 // ------------------------------------------------------------------------------------------------
-// expansion of one node: adjacency fetch (+ the node's own exact distance for the re-rank, PQ modes),
-// filter, distances, sort.  On return s_id/s_d hold the sorted new neighbours, scal[S_NSIZE] their count.
+// stage 5: exact distances of the expanded nodes (compute_L2Dist, bang_search.cu:1254-1299) with
+// coalesced 16-byte loads, 8 lanes per row, two rows in flight per lane group; then the top-k by
+// (exact distance, id) (compute_NearestNeighbours, :1312-1368).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE>
-__device__ __forceinline__ void expand(const SearchArgs& a, const QState& s, uint32_t* bloom, uint32_t parent,
-                                       bool with_medoid, uint32_t cand_slot) {
-  const uint32_t tid = threadIdx.x;
-  const uint8_t* row = row_ptr(a, parent);
-  const uint32_t off = with_medoid ? 1u : 0u;
-  uint32_t nb = kNoNbr;
-  if (tid < kMaxR) nb = ld_nc_u32(row + 4 * tid);
-  if (MODE != kExact && tid >= 96) {
-    // warp 3 (its four 8-lane groups read the same addresses, which coalesce into one request): exact
-    // distance of the expanded node itself (feeds stage 5; the vector sits right behind the adjacency
-    // block in the same HBM row, so it rides the same fetch)
-    const float d = l2_row_8lane<T>(row + kAdjBytes, s.q_f, a.vec_units, tid & 7);
-    if (tid == 96) s.cand_d[cand_slot] = d;
+template <typename T>
+__device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
+  const uint32_t tid = threadIdx.x, t = tid & 7, slot = tid >> 3;
+  float* cd = s.lut;  // the PQ table is dead by now
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+    const uint32_t i0 = b0 + slot, i1 = b0 + 16 + slot;
+    const uint32_t id0 = i0 < n ? s.cand_id[i0] : a.medoid, id1 = i1 < n ? s.cand_id[i1] : a.medoid;
+    const float d0 = l2_row_8lane<T>(row_ptr(a, id0) + kAdjBytes, s.q_f, a.vec_units, t);
+    const float d1 = l2_row_8lane<T>(row_ptr(a, id1) + kAdjBytes, s.q_f, a.vec_units, t);
+    if (t == 0 && i0 < n) cd[i0] = d0;
+    if (t == 0 && i1 < n) cd[i1] = d1;
   }
-  if (tid < kMaxR) s.lst[off + tid] = nb;
-  if (with_medoid && tid == 0) s.lst[0] = a.medoid;
-  const uint32_t deg = __syncthreads_count(tid < kMaxR && nb != kNoNbr);
-  const uint32_t n_list = off + deg;
-  if (tid < 32) filter_list<MODE>(s, bloom, n_list);
   __syncthreads();
-  const uint32_t n = s.scal[S_NSIZE];
-  if (tid == 0) { s.scal[S_SUMDEG] += deg; s.scal[S_NPASS] += n; }
-  if (MODE == kExact) exact_distances<T>(a, s, n);
-  else pq_distances(a, s, n);
-  __syncthreads();
-  sort_neighbours(s, n);
-  __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// stage 5: top-k of the candidate log by (exact distance, id)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void write_topk(const SearchArgs& a, uint32_t q, const uint32_t* ids, const float* d,
-                                           uint32_t n) {
-  const uint32_t tid = threadIdx.x;
   for (uint32_t i = tid; i < n; i += kThreads) {
-    const float di = d[i];
-    const uint32_t idi = ids[i];
+    const float di = cd[i];
+    const uint32_t idi = s.cand_id[i];
     uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; ++j) rank += key_less(d[j], ids[j], di, idi) ? 1u : 0u;
+    for (uint32_t j = 0; j < n; ++j) rank += key_less(cd[j], s.cand_id[j], di, idi) ? 1u : 0u;
     if (rank < a.k) {
       a.out_ids[(size_t)q * a.k + rank] = idi;
       a.out_dists[(size_t)q * a.k + rank] = di;
@@ -554,21 +565,22 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
   uint32_t* bloom = a.bloom + (size_t)blockIdx.x * kBloomWords;
 
   for (;;) {
+    __syncthreads();
     if (tid == 0) s.scal[S_QUERY] = atomicAdd(a.counter, 1u);
     __syncthreads();
     const uint32_t q = s.scal[S_QUERY];
     if (q >= a.Q) break;
 
     // ---- per-query setup: query -> smem, bloom filter cleared, PQ table built in place ----
+    uint32_t my_nb = fetch_adj(a, a.medoid);  // the first hop's adjacency row travels during the setup
     load_query<T>(a, q, s.q_f);
     {
       uint4* b4 = reinterpret_cast<uint4*>(bloom);
       for (uint32_t i = tid; i < kBloomWords / 4; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-      s.scal[S_WSIZE] = 0; s.scal[S_CUR] = 0; s.scal[S_NSIZE] = 0; s.scal[S_NCAND] = 1;
-      s.scal[S_SUMDEG] = 0; s.scal[S_NPASS] = 0; s.scal[S_MARK] = 0x01010101u;
-      s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
+      s.scal[S_CNT0] = 0; s.scal[S_CNT1] = 0; s.scal[S_SUMDEG] = 0; s.scal[S_NPASS] = 0; s.scal[S_POS0] = 0;
+      if (MODE != kExact) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
     }
     __syncthreads();
     if (MODE != kExact) {
@@ -576,126 +588,109 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
       __syncthreads();
     }
 
-    if (MODE == kBase) {
-      // ---- BANG_Base order: A.1 seed, then { merge(prev) ; mark ; expand(parent) ; compute_parent2 } ----
-      expand<T, MODE>(a, s, bloom, a.medoid, true, 0);
-      uint32_t n = s.scal[S_NSIZE];
-      // compute_parent1: closest seeded neighbour that is not the medoid = first such entry of the sorted list
-      bool have = false;
-      uint32_t parent = 0, mark = 0x01010101u;
-      {
-        uint32_t pick = 0xFFFFFFFFu;
-        if (n > 0 && s.s_id[0] != a.medoid) pick = 0;
-        else if (n > 1) pick = 1;
-        if (pick != 0xFFFFFFFFu) { have = true; parent = s.s_id[pick]; mark = parent; }
+    uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1;
+    auto log_parent = [&](uint32_t node) {
+      if (tid == 0) {
+        if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
+        if (a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = node;
       }
-      uint32_t ncand = 1;
-      if (have) { if (tid == 0) s.cand_id[ncand] = parent; ++ncand; }
-      uint32_t iter = 1;
-      __syncthreads();
-      while (have || n > 0) {
-        merge_worklist(a, s, n, iter == 1);
-        {  // mark the node chosen by the previous parent selection (:1711-1714)
-          const uint32_t ws = s.scal[S_WSIZE], cur = s.scal[S_CUR];
-          for (uint32_t j = tid; j < ws; j += kThreads)
-            if (s.wid(cur)[j] == mark) s.wv(cur)[j] = 1;
+      if (ncand < a.cand_cap) ++ncand;
+    };
+
+    if (MODE == kBase) {
+      // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
+      uint32_t par = 1;
+      uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, true, par);
+      Best b = scan_neighbours(s, par, n, a.medoid, true, 0.0f);
+      bool have = b.id != kNone;               // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
+      uint32_t parent = b.id, mark = have ? b.id : 0x01010101u;
+      if (have) log_parent(parent);
+      uint32_t pend_n = n, pend_nb = min(n, a.L), scan_from = 0;
+      while (have || pend_n > 0) {
+        if (have) my_nb = fetch_adj(a, parent);  // in flight during the merge
+        if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
+          ws = merge_worklist(a, s, par, pend_n, pend_nb, ws, iter == 1, mark);
+          scan_from = min(scan_from, s.scal[S_POS0]);
         }
-        __syncthreads();
-        if (have) {
-          expand<T, MODE>(a, s, bloom, parent, false, ncand - 1);
-          n = s.scal[S_NSIZE];
-        } else {
-          n = 0;
-        }
+        fu = scan_unvisited(s, scan_from, ws);
+        scan_from = fu == kNone ? ws : fu;
+        if (have) { par ^= 1u; n = expand<T, MODE>(a, s, bloom, my_nb, false, par); }  // `par` = buffer of the pending list
+        else n = 0u;
         ++iter;
         // compute_parent2 (:1403-1458)
-        float xd = 3.402823E+38f;
-        uint32_t xid = 0;
-        bool hasx = false;
-        if (n > 0 && s.s_id[0] != a.medoid) { hasx = true; xd = s.s_d[0]; xid = s.s_id[0]; }
-        else if (n > 1) { hasx = true; xd = s.s_d[1]; xid = s.s_id[1]; }
-        (void)hasx;
-        const uint32_t u = first_unvisited(s);
-        const uint32_t ws = s.scal[S_WSIZE], cur = s.scal[S_CUR];
+        const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
+        b = scan_neighbours(s, par, n, a.medoid, true, maxd);
+        const bool hasx = b.id != kNone;
         have = false;
-        if (u != 0xFFFFFFFFu) {
+        if (fu != kNone) {
           have = true;
-          if (xd < s.wd(cur)[u]) { parent = xid; mark = xid; }
-          else { parent = s.wid(cur)[u]; if (tid == 0) s.wv(cur)[u] = 1; }
-        } else if (ws > 0 && xd < s.wd(cur)[ws - 1]) {
-          have = true; parent = xid; mark = xid;
+          if (hasx && b.d < s.w_d[fu]) { parent = b.id; mark = b.id; }
+          else { parent = s.w_id[fu]; if (tid == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
+        } else if (ws > 0 && hasx && b.d < maxd) {
+          have = true; parent = b.id; mark = b.id;
         }
-        if (have) { if (tid == 0 && ncand < a.cand_cap) s.cand_id[ncand] = parent; if (ncand < a.cand_cap) ++ncand; }
-        __syncthreads();
+        if (have) log_parent(parent);
+        pend_n = n;
+        pend_nb = n ? admit_count(b.below, n, ws, a.L) : 0u;
         if (iter == a.max_iter - 1) break;
       }
-      if (tid == 0) s.scal[S_NCAND] = ncand;
-      // candidates selected but never expanded (cap reached) still need their exact distance
-      __syncthreads();
-      {
-        const uint32_t done = (iter == a.max_iter - 1 && have) ? ncand - 1 : ncand;
-        const uint32_t t = tid & 7, slot = tid >> 3;
-        for (uint32_t b0 = done; b0 < ncand; b0 += 16) {  // uniform trip count: shuffles need whole warps
-          const uint32_t i = b0 + slot;
-          const uint32_t id = i < ncand ? s.cand_id[i] : a.medoid;
-          const float d = l2_row_8lane<T>(row_ptr(a, id) + kAdjBytes, s.q_f, a.vec_units, t);
-          if (t == 0 && i < ncand) s.cand_d[i] = d;
-        }
-      }
-      __syncthreads();
-      write_topk(a, q, s.cand_id, s.cand_d, ncand);
+      rerank_and_write<T>(a, s, q, ncand);
     } else {
-      // ---- BANG_Inmemory / BANG_Exactdistance order: { expand(parent) ; merge ; pick first unvisited } ----
-      uint32_t parent = a.medoid, iter = 1, ncand = 1;
-      bool capped = false;
+      // ---- BANG_Inmemory / BANG_Exactdistance (A.2', A.2''): { expand(parent) ; merge ; first unvisited } ----
+      // The first unvisited entry after the merge is decided before it: the closest new entry if it is
+      // admitted and not farther than the first unvisited old entry (new goes before old on ties).
+      uint32_t parent = a.medoid;
       for (;;) {
-        expand<T, MODE>(a, s, bloom, parent, iter == 1, ncand - 1);
-        merge_worklist(a, s, s.scal[S_NSIZE], iter == 1);
-        const uint32_t u = first_unvisited(s);
-        if (u == 0xFFFFFFFFu) break;
-        const uint32_t cur = s.scal[S_CUR];
-        parent = s.wid(cur)[u];
-        if (tid == 0) {
-          s.wv(cur)[u] = 1;
-          if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = parent;
-          if (a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = parent;
+        const bool first = iter == 1;
+        const uint32_t par = iter & 1u;
+        const uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, first, par);
+        const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
+        const Best b = scan_neighbours(s, par, n, a.medoid, first, maxd);
+        uint32_t nb;
+        bool have = false, from_new = false;
+        if (first) {
+          nb = min(n, a.L);
+          const uint32_t rank_x = (b.med_in && key_less(b.med_d, a.medoid, b.d, b.id)) ? 1u : 0u;
+          if (b.id != kNone && rank_x < nb) { have = true; from_new = true; parent = b.id; }
+        } else {
+          nb = n ? admit_count(b.below, n, ws, a.L) : 0u;
+          if (nb > 0 && (fu == kNone || b.d <= s.w_d[fu])) { have = true; from_new = true; parent = b.id; }
+          else if (fu != kNone) { have = true; parent = s.w_id[fu]; }
         }
-        if (ncand < a.cand_cap) ++ncand;
-        __syncthreads();
-        if (iter == a.max_iter - 1) { capped = true; break; }
+        if (!have) break;  // nothing unvisited and nothing admitted: the merge would be a no-op
+        uint32_t scan_from = fu == kNone ? ws : fu;
+        if (!from_new) { if (tid == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
+        log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
+        const bool capped = iter == a.max_iter - 1;
+        if (!capped) my_nb = fetch_adj(a, parent);  // in flight during the merge
+        if (nb > 0) {
+          ws = merge_worklist(a, s, par, n, nb, ws, first, from_new ? parent : kNone);
+          scan_from = min(scan_from, s.scal[S_POS0]);
+        }
+        fu = scan_unvisited(s, scan_from, ws);
+        if (capped) break;
         ++iter;
       }
       if (MODE == kExact) {
         // top-k = head of the worklist (Exact parANN.cu:1273-1276)
-        const uint32_t ws = s.scal[S_WSIZE], cur = s.scal[S_CUR];
+        __syncthreads();
         for (uint32_t r = tid; r < a.k; r += kThreads) {
-          a.out_ids[(size_t)q * a.k + r] = r < ws ? (uint64_t)s.wid(cur)[r] : 0xFFFFFFFFull;
-          a.out_dists[(size_t)q * a.k + r] = r < ws ? s.wd(cur)[r] : 3.402823466e+38f;
+          a.out_ids[(size_t)q * a.k + r] = r < ws ? (uint64_t)s.w_id[r] : 0xFFFFFFFFull;
+          a.out_dists[(size_t)q * a.k + r] = r < ws ? s.w_d[r] : 3.402823466e+38f;
         }
       } else {
-        __syncthreads();
-        if (capped) {  // the last logged parent was never expanded: score it now
-          if (tid < 32) {
-            const float d = l2_row_8lane<T>(row_ptr(a, s.cand_id[ncand - 1]) + kAdjBytes, s.q_f, a.vec_units, tid & 7);
-            if (tid == 0) s.cand_d[ncand - 1] = d;
-          }
-          __syncthreads();
-        }
-        write_topk(a, q, s.cand_id, s.cand_d, ncand);
+        rerank_and_write<T>(a, s, q, ncand);
       }
-      if (tid == 0) s.scal[S_NCAND] = ncand;
     }
-    __syncthreads();
     if (tid == 0) {
       if (a.dump_ids) {
         a.dump_ids[(size_t)q * a.dump_stride] = a.medoid;
-        a.dump_n[q] = min(s.scal[S_NCAND], a.dump_stride);
+        a.dump_n[q] = min(ncand, a.dump_stride);
       }
-      if (a.st_hops) a.st_hops[q] = s.scal[S_NCAND];
+      if (a.st_hops) a.st_hops[q] = ncand;
       if (a.st_sumdeg) a.st_sumdeg[q] = s.scal[S_SUMDEG];
       if (a.st_npass) a.st_npass[q] = s.scal[S_NPASS];
     }
-    __syncthreads();
   }
 }
 
