@@ -1,20 +1,28 @@
 // search_kernel.cuh — the fused, persistent, per-query-block traversal kernel for sm_100a.
 //
-// One CTA (128 threads) owns one query at a time and walks the whole greedy search for it without
-// leaving the SM: PQ table build (stage 1) -> { adjacency fetch, visited filter (stage 4a), PQ/exact
-// distances (stage 3), parent selection (stage 2), (dist,id) sort + worklist merge (stage 4b) }* ->
-// exact re-rank + top-k (stage 5).  CTAs are persistent: the grid is sized to the number of resident
-// CTAs and each CTA pulls query indices from a global counter.  What the reference does with ~5 kernel
-// launches, 2 memsets, up to 5 PCIe copies and 3 stream syncs per hop (bang_search.cu:701-958) is one
-// launch here; the LUT, worklist, candidate log and neighbour lists never leave shared memory.
+// One warp owns one query at a time and walks the whole greedy search for it without leaving the SM:
+// PQ table build (stage 1) -> { adjacency fetch, visited filter (stage 4a), PQ/exact distances
+// (stage 3), parent selection (stage 2), (dist,id) sort + worklist merge (stage 4b) }* -> exact re-rank
+// + top-k (stage 5).  CTAs (= one warp) are persistent: the grid is sized to the number of resident CTAs
+// and each pulls query indices from a global counter.  What the reference does with ~5 kernel launches,
+// 2 memsets, up to 5 PCIe copies and 3 stream syncs per hop (bang_search.cu:701-958) is one launch here;
+// the LUT, worklist, candidate log and neighbour lists never leave shared memory.
 //
-// The search is a dependent pointer chase, so the kernel is organised around the per-hop critical path
-// (ncu: profiles/r1_*): each warp runs its own slice of the expansion (16 adjacency ids: hash, one L2
-// load per bloom word, fire-and-forget `red.or` to set, 8 lanes per accepted candidate for the
-// distance) with two CTA barriers per hop; the next node to expand is decided from the unsorted
-// distances BEFORE the sort/merge (it is the smaller of the best new candidate and the first unvisited
-// worklist entry — exactly what the merge would produce) and its adjacency row is requested at once, so
-// the merge overlaps the DRAM latency of the next hop.
+// Why one warp: the search is a dependent pointer chase whose per-hop work is tiny (64 hashes, ~10 PQ
+// distances, a 150-entry merge).  Residency is capped by the 32 KB fp32 LUT per query (6 queries per
+// SM), so the lever is the per-hop critical path, not occupancy.  ncu on the 4-warp versions
+// (profiles/r1a, r1b) showed 22-40 % of the samples in CTA barriers and 586 instructions per warp-hop,
+// mostly redundant; a single warp needs no CTA barrier (only __syncwarp), reduces with redux.sync, and
+// leaves the issue slots to the other five queries of the SM.  Per hop:
+//   * the adjacency row (256 B) was requested at the end of the previous hop, one 8-byte load per lane;
+//   * visited filter with snapshot semantics: 4 bloom words per lane in one L2 round trip, insertion
+//     by fire-and-forget `red.or` (nothing waits on it);
+//   * 8 lanes per accepted candidate for the distance, 16 candidates' code loads in flight;
+//   * the next node to expand is decided from the unsorted distances BEFORE the sort/merge (it is the
+//     smaller of the best admitted new candidate and the first unvisited worklist entry — exactly what
+//     the merge would produce) and its adjacency row is requested at once, so the merge overlaps the
+//     DRAM latency of the next hop;
+//   * in-place merge, 32 entries at a time from the tail, only from the first insertion point on.
 //
 // Semantics are the reference's with the deterministic choices documented in
 // oracle/bang_oracle.c; the oracle is bit-exact with this kernel (ORDER_GPU).
@@ -29,7 +37,7 @@
 
 namespace bang {
 
-constexpr int kThreads = 128;           // threads per query CTA
+constexpr int kThreads = 32;            // one warp per query (see the header comment)
 constexpr int kMaxR = 64;               // MAX_R, bang_search.cu:35
 constexpr int kListCap = kMaxR + 8;     // medoid + R neighbours, padded
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
@@ -184,14 +192,32 @@ __device__ __forceinline__ float l2_row_8lane(const uint8_t* vec, const float* q
   return tree8(acc);
 }
 
+// Two rows at once (same arithmetic per row as l2_row_8lane, loads interleaved for memory-level parallelism).
+template <typename T>
+__device__ __forceinline__ void l2_two_rows_8lane(const uint8_t* va, const uint8_t* vb, const float* q_f, uint32_t units,
+                                                  uint32_t t, float* da, float* db) {
+  constexpr int E = Elem<T>::kPerUnit;
+  float acc_a = 0.0f, acc_b = 0.0f;
+  for (uint32_t u = t; u < units; u += 8) {
+    const uint4 ra = ld_nc_u4(va + (size_t)u * 16);
+    const uint4 rb = ld_nc_u4(vb + (size_t)u * 16);
+    float f[E];
+    Elem<T>::unpack(ra, f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const float d = __fsub_rn(f[e], q_f[u * E + e]); acc_a = __fmaf_rn(d, d, acc_a); }
+    Elem<T>::unpack(rb, f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const float d = __fsub_rn(f[e], q_f[u * E + e]); acc_b = __fmaf_rn(d, d, acc_b); }
+  }
+  *da = tree8(acc_a);
+  *db = tree8(acc_b);
+}
+
 // ------------------------------------------------------------------------------------------------
 // shared-memory state of one query
 // ------------------------------------------------------------------------------------------------
-constexpr int kWarps = kThreads / 32;         // 4
-constexpr int kIdsPerWarp = kMaxR / kWarps;   // 16 adjacency ids per warp (+ the medoid in warp 0 on the first hop)
-constexpr int kStage = 20;                    // per-warp staging slots for accepted ids (<= 17 used)
-constexpr int kWEnt = (BANG_B200_KERNEL_MAX_L + kThreads - 1) / kThreads;  // worklist entries per thread in a merge
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kFull = 0xffffffffu;
 
 struct QState {
   float* q_f;        // [vec_units * E] query as fp32, zero padded
@@ -199,15 +225,12 @@ struct QState {
   float* w_d;        // worklist [w_cap], sorted by distance
   uint32_t* w_id;
   uint8_t* w_v;      // visited flags
-  uint32_t* n_id0;   // filtered neighbours, two buffers (hop parity) of kListCap
-  float* n_d0;
-  uint32_t* wstage;  // [kWarps][kStage]
+  uint32_t* n_id;    // [kListCap] filtered neighbours of this hop, unordered
+  float* n_d;
+  uint32_t* s_id;    // [kListCap] the admitted ones, sorted by (dist, id)
+  float* s_d;
   uint32_t* cand_id; // [cand_cap] expanded-node log (PQ modes)
-  uint32_t* scal;
-  __device__ __forceinline__ uint32_t* n_id(uint32_t par) const { return n_id0 + par * kListCap; }
-  __device__ __forceinline__ float* n_d(uint32_t par) const { return n_d0 + par * kListCap; }
 };
-enum { S_CNT0 = 0, S_CNT1, S_QUERY, S_SUMDEG, S_NPASS, S_POS0, S_COUNT = 8 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -222,11 +245,9 @@ __host__ __device__ inline size_t smem_bytes(int mode, uint32_t n_chunks, uint32
   size_t b = 0;
   b += align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);
   b += lut_region_bytes(mode, n_chunks, cand_cap);
-  b += align_up(L, 16) * 9;                         // worklist: dist + id + visited
-  b += (size_t)kListCap * 4 * 2 * 2;                // neighbour lists, two parities
-  b += (size_t)kWarps * kStage * 4;
+  b += align_up(L, 16) * 9;            // worklist: dist + id + visited
+  b += (size_t)kListCap * 4 * 4;       // neighbour list + sorted admitted list
   if (mode != kExact) b += align_up((size_t)cand_cap * 4, 16);
-  b += S_COUNT * 4;
   return align_up(b, 16);
 }
 
@@ -239,32 +260,38 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
   s.w_d = (float*)(base + o); o += wcap * 4;
   s.w_id = (uint32_t*)(base + o); o += wcap * 4;
   s.w_v = (uint8_t*)(base + o); o += wcap;
-  s.n_id0 = (uint32_t*)(base + o); o += (size_t)kListCap * 4 * 2;
-  s.n_d0 = (float*)(base + o); o += (size_t)kListCap * 4 * 2;
-  s.wstage = (uint32_t*)(base + o); o += (size_t)kWarps * kStage * 4;
-  s.cand_id = (uint32_t*)(base + o); if (mode != kExact) o += align_up((size_t)a.cand_cap * 4, 16);
-  s.scal = (uint32_t*)(base + o);
+  s.n_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
+  s.n_d = (float*)(base + o); o += (size_t)kListCap * 4;
+  s.s_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
+  s.s_d = (float*)(base + o); o += (size_t)kListCap * 4;
+  s.cand_id = (uint32_t*)(base + o);
 }
 
 // ------------------------------------------------------------------------------------------------
 // stage 1: per-query PQ distance table into shared memory (or global for the standalone kernel)
 // tbl[c][k] = sum_{j in chunk c} (pivT[j][k] - (q[j] - centroid[j]))^2, j ascending, fmaf
+// (populate_pqDist_par, bang_search.cu:1118-1129).  Lane l owns centres 4l..4l+3 and 128+4l..128+4l+3:
+// two coalesced 512-byte requests per dimension, 8 independent accumulators per lane.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void build_pq_table(const SearchArgs& a, const float* q_f, float* tbl /*[m][256]*/) {
-  const uint32_t tid = threadIdx.x;
-  // 128 threads x 2 consecutive centres each (float2, coalesced over pivT rows)
+  const uint32_t lane = threadIdx.x & 31;
   for (uint32_t c = 0; c < a.n_chunks; ++c) {
     const uint32_t j0 = a.chunk_off[c], j1 = a.chunk_off[c + 1];
-    float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll 8
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+#pragma unroll 4
     for (uint32_t j = j0; j < j1; ++j) {
       const float qc = __fsub_rn(q_f[j], __ldg(a.centroid + j));
-      const float2 p = __ldg(reinterpret_cast<const float2*>(a.pivT + (size_t)j * 256) + tid);
-      const float d0 = __fsub_rn(p.x, qc), d1 = __fsub_rn(p.y, qc);
-      acc0 = __fmaf_rn(d0, d0, acc0);
-      acc1 = __fmaf_rn(d1, d1, acc1);
+      const float4* row = reinterpret_cast<const float4*>(a.pivT + (size_t)j * 256);
+      const float4 p0 = __ldg(row + lane), p1 = __ldg(row + 32 + lane);
+      const float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = __fsub_rn(v[i], qc); acc[i] = __fmaf_rn(d, d, acc[i]); }
     }
-    reinterpret_cast<float2*>(tbl + (size_t)c * 256)[tid] = make_float2(acc0, acc1);
+    float4* out = reinterpret_cast<float4*>(tbl + (size_t)c * 256);
+    out[lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    out[32 + lane] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
@@ -275,101 +302,111 @@ __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, floa
   for (uint32_t i = threadIdx.x; i < n; i += kThreads) q_f[i] = i < a.q_dim ? (float)src[i] : 0.0f;
 }
 
-// adjacency prefetch: lanes 0..15 of warp w request ids [16w, 16w+16) of `node`'s HBM row
-__device__ __forceinline__ uint32_t fetch_adj(const SearchArgs& a, uint32_t node) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t v = kNoNbr;
-  if (lane < (uint32_t)kIdsPerWarp) v = ld_nc_u32(row_ptr(a, node) + 4 * (kIdsPerWarp * warp + lane));
-  return v;
+// adjacency prefetch: lane l requests neighbour slots 2l and 2l+1 of `node`'s HBM row (one 256-byte request)
+__device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node) {
+  uint2 r;
+  const uint8_t* p = row_ptr(a, node) + 8 * (threadIdx.x & 31);
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+struct BloomPos { uint32_t w1, b1, w2, b2; };
+template <int MODE>
+__device__ __forceinline__ BloomPos bloom_pos(uint32_t id) {
+  BloomPos p;
+  const uint32_t p1 = hash1(id);
+  p.w1 = p1 >> 5; p.b1 = 1u << (p1 & 31);
+  if (MODE == kExact) { p.w2 = p.w1; p.b2 = p.b1; }  // BANG_Exactdistance tests hash 1 only (parANN.cu:1040-1066)
+  else { const uint32_t p2 = hash2(id); p.w2 = p2 >> 5; p.b2 = 1u << (p2 & 31); }
+  return p;
 }
 
 // ------------------------------------------------------------------------------------------------
-// expansion of one node = stages 4a + 3.  Every warp owns 16 adjacency ids (already requested by
-// fetch_adj): visited filter with snapshot semantics (all tests of a list precede all insertions — one
-// barrier), then 8 lanes per accepted candidate for the PQ / exact distance.  Accepted (id, dist) pairs
-// land unordered in the neighbour buffer of this hop's parity; returns their count.
-//   filter   neighbor_filtering_new + hashFn1_d/2_d   bang_search.cu:1140-1189 (Exact: hash 1 only)
-//   PQ dist  compute_neighborDist_par                 bang_search.cu:1201-1241: lane t owns chunks t, t+8, ...
-//            ascending, partials combined by the 8-lane tree.  The HBM code rows are permuted at load so
-//            lane t's chunks 32g+t, 32g+8+t, 32g+16+t, 32g+24+t are one aligned 32-bit word: one 32-byte
-//            sector per candidate per 32 chunks, fully used.
+// expansion of one node = stages 4a + 3.  The adjacency row is already in registers (fetch_adj).
+//   filter   neighbor_filtering_new + hashFn1_d/2_d   bang_search.cu:1140-1189 — snapshot semantics: all
+//            tests of a list precede all insertions (the lock-step outcome of the reference's kernel).
+//            On the first hop the filter is empty, so [medoid] ++ adj(medoid) is accepted wholesale.
+//   PQ dist  compute_neighborDist_par                 bang_search.cu:1201-1241: lane t of an 8-lane group
+//            owns chunks t, t+8, ... ascending, partials combined by the 8-lane tree.  The HBM code rows
+//            are permuted at load so lane t's chunks 32g+t, 32g+8+t, 32g+16+t, 32g+24+t are one aligned
+//            32-bit word: one 32-byte sector per candidate per 32 chunks, fully used.
 //   exact    compute_neighborDist_par                 BANG_Exactdistance/parANN.cu:1139-1179
+// Returns the number of accepted candidates; n_id/n_d hold them unordered; *deg_out = degree of the node.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE>
-__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint32_t* bloom, uint32_t my_nb, bool first,
-                                           uint32_t par) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t id = kNoNbr;
-  if (lane < (uint32_t)kIdsPerWarp) id = my_nb;
-  else if (first && warp == 0 && lane == (uint32_t)kIdsPerWarp) id = a.medoid;  // [medoid] ++ adj(medoid) on the first hop
-  const bool valid = id != kNoNbr;
-  uint32_t w1 = 0, b1 = 0, w2 = 0, b2 = 0;
-  bool acc = false;
-  if (valid) {
-    const uint32_t p1 = hash1(id);
-    w1 = p1 >> 5; b1 = 1u << (p1 & 31);
-    if (MODE == kExact) {
-      acc = (__ldcg(bloom + w1) & b1) == 0;
-    } else {
-      const uint32_t p2 = hash2(id);
-      w2 = p2 >> 5; b2 = 1u << (p2 & 31);
-      const uint32_t x1 = __ldcg(bloom + w1), x2 = __ldcg(bloom + w2);
-      acc = !((x1 & b1) && (x2 & b2));
+__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint32_t* bloom, uint2 nb2, bool first,
+                                           uint32_t* deg_out) {
+  const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+  const uint32_t id0 = nb2.x, id1 = nb2.y;
+  const bool v0 = id0 != kNoNbr, v1 = id1 != kNoNbr;
+  const BloomPos p0 = bloom_pos<MODE>(id0), p1 = bloom_pos<MODE>(id1);
+  bool acc0 = v0, acc1 = v1;
+  if (!first) {
+    uint32_t x01 = 0, x02 = 0, x11 = 0, x12 = 0;
+    if (v0) { x01 = __ldcg(bloom + p0.w1); if (MODE != kExact) x02 = __ldcg(bloom + p0.w2); }
+    if (v1) { x11 = __ldcg(bloom + p1.w1); if (MODE != kExact) x12 = __ldcg(bloom + p1.w2); }
+    if (MODE == kExact) { acc0 = v0 && !(x01 & p0.b1); acc1 = v1 && !(x11 & p1.b1); }
+    else { acc0 = v0 && !((x01 & p0.b1) && (x02 & p0.b2)); acc1 = v1 && !((x11 & p1.b1) && (x12 & p1.b2)); }
+  }
+  __syncwarp();  // every test precedes every insertion
+  if (acc0) { atomicOr(bloom + p0.w1, p0.b1); if (MODE != kExact) atomicOr(bloom + p0.w2, p0.b2); }  // RED.OR: results unused
+  if (acc1) { atomicOr(bloom + p1.w1, p1.b1); if (MODE != kExact) atomicOr(bloom + p1.w2, p1.b2); }
+  uint32_t pre = 0;
+  if (first) {
+    pre = 1;
+    if (lane == 0) {
+      const BloomPos pm = bloom_pos<MODE>(a.medoid);
+      atomicOr(bloom + pm.w1, pm.b1);
+      if (MODE != kExact) atomicOr(bloom + pm.w2, pm.b2);
+      s.n_id[0] = a.medoid;
     }
   }
-  // all tests of this list are done before any insertion (also counts the degree for the statistics)
-  const uint32_t deg = __syncthreads_count(valid && lane < (uint32_t)kIdsPerWarp);
-  if (acc) {  // results unused -> RED.OR, nothing waits on them
-    atomicOr(bloom + w1, b1);
-    if (MODE != kExact) atomicOr(bloom + w2, b2);
-  }
-  const uint32_t amask = __ballot_sync(0xffffffffu, acc);
-  const uint32_t cnt = __popc(amask);
-  uint32_t base = 0;
-  if (lane == 0 && cnt) base = atomicAdd(&s.scal[S_CNT0 + par], cnt);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  uint32_t* stage = s.wstage + warp * kStage;
-  if (acc) stage[__popc(amask & ((1u << lane) - 1u))] = id;
+  const uint32_t m0 = __ballot_sync(kFull, acc0), m1 = __ballot_sync(kFull, acc1);
+  const uint32_t c0 = __popc(m0);
+  const uint32_t n = pre + c0 + __popc(m1);
+  if (acc0) s.n_id[pre + __popc(m0 & lt)] = id0;
+  if (acc1) s.n_id[pre + c0 + __popc(m1 & lt)] = id1;
+  *deg_out = __popc(__ballot_sync(kFull, v0)) + __popc(__ballot_sync(kFull, v1));
   __syncwarp();
-  uint32_t* n_id = s.n_id(par);
-  float* n_d = s.n_d(par);
-  const uint32_t t = lane & 7, g = lane >> 3;  // 4 candidates per warp pass
-  constexpr int kPass = (kIdsPerWarp + 1 + 3) / 4;  // 5
+  const uint32_t t = lane & 7, g = lane >> 3;  // 4 candidates per pass
   if (MODE == kExact) {
-    for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
-      const uint32_t k = k0 + g;
-      const uint32_t cid = k < cnt ? stage[k] : a.medoid;
-      const float d = l2_row_8lane<T>(row_ptr(a, cid) + kAdjBytes, s.q_f, a.vec_units, t);
-      if (t == 0 && k < cnt) { n_id[base + k] = cid; n_d[base + k] = d; }
+    for (uint32_t k0 = 0; k0 < n; k0 += 8) {  // two rows in flight per lane group
+      const uint32_t ka = k0 + g, kb = k0 + 4 + g;
+      const uint32_t ca = ka < n ? s.n_id[ka] : a.medoid, cb = kb < n ? s.n_id[kb] : a.medoid;
+      float da, db;
+      l2_two_rows_8lane<T>(row_ptr(a, ca) + kAdjBytes, row_ptr(a, cb) + kAdjBytes, s.q_f, a.vec_units, t, &da, &db);
+      if (t == 0 && ka < n) s.n_d[ka] = da;
+      if (t == 0 && kb < n) s.n_d[kb] = db;
     }
   } else if (a.n_chunks <= 32) {
-    uint32_t w[kPass], cid[kPass];
+    for (uint32_t k0 = 0; k0 < n; k0 += 16) {  // 16 candidates' code words in flight
+      uint32_t w[4];
 #pragma unroll
-    for (int p = 0; p < kPass; ++p) {
-      const uint32_t k = p * 4 + g;
-      w[p] = 0; cid[p] = 0;
-      if (k < cnt) { cid[p] = stage[k]; w[p] = ld_nc_u32(a.codes + (size_t)cid[p] * a.code_stride + 4 * t); }
-    }
+      for (int p = 0; p < 4; ++p) {
+        const uint32_t k = k0 + p * 4 + g;
+        w[p] = 0;
+        if (k < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[k] * a.code_stride + 4 * t);
+      }
 #pragma unroll
-    for (int p = 0; p < kPass; ++p) {
-      if (p * 4 < (int)cnt) {  // warp-uniform
-        const uint32_t k = p * 4 + g;
-        float sum = 0.0f;
+      for (int p = 0; p < 4; ++p) {
+        if (k0 + p * 4 < n) {  // warp-uniform
+          const uint32_t k = k0 + p * 4 + g;
+          float sum = 0.0f;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t c = t + 8 * b;
-          if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((w[p] >> (8 * b)) & 0xff)]);
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t c = t + 8 * b;
+            if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((w[p] >> (8 * b)) & 0xff)]);
+          }
+          sum = tree8(sum);
+          if (t == 0 && k < n) s.n_d[k] = sum;
         }
-        sum = tree8(sum);
-        if (t == 0 && k < cnt) { n_id[base + k] = cid[p]; n_d[base + k] = sum; }
       }
     }
   } else {
     const uint32_t groups = (a.n_chunks + 31) >> 5;
-    for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
+    for (uint32_t k0 = 0; k0 < n; k0 += 4) {
       const uint32_t k = k0 + g;
-      const uint32_t cid = k < cnt ? stage[k] : 0u;
-      const uint8_t* row = a.codes + (size_t)cid * a.code_stride + 4 * t;
+      const uint8_t* row = a.codes + (size_t)(k < n ? s.n_id[k] : 0u) * a.code_stride + 4 * t;
       float sum = 0.0f;
       for (uint32_t gg = 0; gg < groups; gg += 2) {
         const uint32_t wa = ld_nc_u32(row + gg * 32);
@@ -386,131 +423,48 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
         }
       }
       sum = tree8(sum);
-      if (t == 0 && k < cnt) { n_id[base + k] = cid; n_d[base + k] = sum; }
+      if (t == 0 && k < n) s.n_d[k] = sum;
     }
   }
-  __syncthreads();
-  const uint32_t n = s.scal[S_CNT0 + par];
-  if (tid == 0) {
-    s.scal[S_CNT0 + (par ^ 1u)] = 0;  // next hop's counter; its last readers passed the barrier above
-    s.scal[S_SUMDEG] += deg;
-    s.scal[S_NPASS] += n;
-  }
+  __syncwarp();
   return n;
 }
 
-// (dist, id)-minimum of the unsorted neighbour list, the number of entries closer than `maxd`, and the
-// medoid's distance if it is in the list.  Every warp computes the same values redundantly from shared
-// memory, so no barrier is needed to publish the decision that follows.
+// (dist, id)-minimum of the unsorted neighbour list (optionally skipping the medoid), the number of
+// entries closer than `maxd`, and the medoid's distance if present.  Distances are >= +0, so their bit
+// patterns order like the floats and redux.sync (min/add over the warp) does the reductions.
 struct Best { float d; uint32_t id; uint32_t below; float med_d; bool med_in; };
-__device__ __forceinline__ Best scan_neighbours(const QState& s, uint32_t par, uint32_t n, uint32_t medoid, bool skip_medoid,
-                                                float maxd) {
+__device__ __forceinline__ Best scan_neighbours(const QState& s, uint32_t n, uint32_t medoid, bool skip_medoid, float maxd) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t* n_id = s.n_id(par);
-  const float* n_d = s.n_d(par);
-  Best b{3.402823466e+38f, kNone, 0u, 0.0f, false};
+  uint32_t bd = 0x7F7FFFFFu /* FLT_MAX */, bid = kNone, below = 0, md = 0;
+  bool mi = false;
   for (uint32_t i = lane; i < n; i += 32) {
-    const float d = n_d[i];
-    const uint32_t id = n_id[i];
-    b.below += d < maxd ? 1u : 0u;
-    if (id == medoid) { b.med_in = true; b.med_d = d; if (skip_medoid) continue; }
-    if (key_less(d, id, b.d, b.id)) { b.d = d; b.id = id; }
+    const float d = s.n_d[i];
+    const uint32_t id = s.n_id[i], db = __float_as_uint(d);
+    below += d < maxd ? 1u : 0u;
+    if (id == medoid) { mi = true; md = db; if (skip_medoid) continue; }
+    if (db < bd || (db == bd && id < bid)) { bd = db; bid = id; }
   }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, b.d, off);
-    const uint32_t oid = __shfl_xor_sync(0xffffffffu, b.id, off);
-    if (key_less(od, oid, b.d, b.id)) { b.d = od; b.id = oid; }
-    b.below += __shfl_xor_sync(0xffffffffu, b.below, off);
-    const float omd = __shfl_xor_sync(0xffffffffu, b.med_d, off);
-    const bool omi = __shfl_xor_sync(0xffffffffu, (int)b.med_in, off) != 0;
-    if (omi) { b.med_in = true; b.med_d = omd; }
-  }
+  Best b;
+  const uint32_t dmin = __reduce_min_sync(kFull, bd);
+  b.id = __reduce_min_sync(kFull, bd == dmin ? bid : kNone);
+  b.d = __uint_as_float(dmin);
+  b.below = __reduce_add_sync(kFull, below);
+  const uint32_t mm = __ballot_sync(kFull, mi);
+  b.med_in = mm != 0;
+  b.med_d = __uint_as_float(__shfl_sync(kFull, md, mm ? __ffs(mm) - 1 : 0));
   return b;
 }
 
-// first unvisited worklist entry at or after `start` (warp-redundant, shared memory only)
+// first unvisited worklist entry at or after `start`
 __device__ __forceinline__ uint32_t scan_unvisited(const QState& s, uint32_t start, uint32_t ws) {
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t b0 = start; b0 < ws; b0 += 32) {
     const uint32_t j = b0 + lane;
-    const uint32_t m = __ballot_sync(0xffffffffu, j < ws && s.w_v[j] == 0);
+    const uint32_t m = __ballot_sync(kFull, j < ws && s.w_v[j] == 0);
     if (m) return b0 + (uint32_t)__ffs(m) - 1u;
   }
   return kNone;
-}
-
-// ------------------------------------------------------------------------------------------------
-// stage 4b: (dist, id) sort of the new neighbours + merge into the worklist, in place.
-// compute_BestLSets_par_sort_msort + compute_BestLSets_par_merge (bang_search.cu:1533-1585, 1605-1715):
-// only the `nb` closest new entries take part (nb as the reference computes nbrsBound); a new entry
-// goes before old entries of equal distance; the list is truncated to L.  New entries are unvisited,
-// except `flag_id` (the node just chosen for expansion / the reference's d_mark) and, in the first
-// merge, the medoid.  Returns the new size; scal[S_POS0] = position of the closest new entry.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QState& s, uint32_t par, uint32_t n, uint32_t nb,
-                                                   uint32_t ws, bool first, uint32_t flag_id) {
-  const uint32_t tid = threadIdx.x;
-  uint32_t* s_id = s.n_id(par ^ 1u);  // the other parity's buffer is idle until the next hop's expansion
-  float* s_d = s.n_d(par ^ 1u);
-  const uint32_t* n_id = s.n_id(par);
-  const float* n_d = s.n_d(par);
-  if (tid < n) {
-    const float d = n_d[tid];
-    const uint32_t id = n_id[tid];
-    uint32_t r = 0;
-    for (uint32_t j = 0; j < n; ++j) r += key_less(n_d[j], n_id[j], d, id) ? 1u : 0u;
-    if (r < nb) { s_d[r] = d; s_id[r] = id; }
-  }
-  __syncthreads();
-  if (first) {  // iter == 1 branch (:1636-1646): the worklist is the head of the sorted list
-    if (tid < nb) {
-      const uint32_t id = s_id[tid];
-      s.w_d[tid] = s_d[tid];
-      s.w_id[tid] = id;
-      s.w_v[tid] = (id == a.medoid || id == flag_id) ? 1 : 0;
-    }
-    if (tid == 0) s.scal[S_POS0] = 0;
-    __syncthreads();
-    return nb;
-  }
-  const uint32_t newsize = min(ws + nb, a.L);
-  float od[kWEnt];
-  uint32_t oid[kWEnt], opos[kWEnt];
-  uint8_t ov[kWEnt];
-#pragma unroll
-  for (int e = 0; e < kWEnt; ++e) {  // old entry: position = index + upper_bound(new, d)
-    const uint32_t j = tid + e * kThreads;
-    opos[e] = kNone;
-    if (j < ws) {
-      od[e] = s.w_d[j]; oid[e] = s.w_id[j]; ov[e] = s.w_v[j];
-      uint32_t lo = 0, hi = nb;
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (od[e] >= s_d[mid]) lo = mid + 1; else hi = mid;
-      }
-      opos[e] = j + lo;
-    }
-  }
-  uint32_t npos = kNone, nid = 0;
-  float nd = 0.0f;
-  if (tid < nb) {  // new entry: position = index + lower_bound(W, d)  (new before old on ties)
-    nd = s_d[tid]; nid = s_id[tid];
-    uint32_t lo = 0, hi = ws;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (nd <= s.w_d[mid]) hi = mid; else lo = mid + 1;
-    }
-    npos = lo + tid;
-    if (tid == 0) s.scal[S_POS0] = npos;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int e = 0; e < kWEnt; ++e)
-    if (opos[e] < newsize) { s.w_d[opos[e]] = od[e]; s.w_id[opos[e]] = oid[e]; s.w_v[opos[e]] = ov[e]; }
-  if (npos < newsize) { s.w_d[npos] = nd; s.w_id[npos] = nid; s.w_v[npos] = (nid == flag_id) ? 1 : 0; }
-  __syncthreads();
-  return newsize;
 }
 
 // number of new entries the reference's merge admits (nbrsBound, bang_search.cu:1651-1656)
@@ -519,37 +473,128 @@ __device__ __forceinline__ uint32_t admit_count(uint32_t below, uint32_t n, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// stage 4b: (dist, id) sort of the new neighbours + merge into the worklist, in place.
+// compute_BestLSets_par_sort_msort + compute_BestLSets_par_merge (bang_search.cu:1533-1585, 1605-1715):
+// only the `nb` closest new entries take part (nb as the reference computes nbrsBound); a new entry
+// goes before old entries of equal distance; the list is truncated to L.  New entries are unvisited,
+// except `flag_id` (the node just chosen for expansion / the reference's d_mark) and, in the first
+// merge, the medoid.  Old entries move to index + upper_bound(new, d), 32 at a time from the tail and
+// only from the first insertion point on, so nothing is overwritten before it is read.
+// Returns the new size; *pos0 = position of the closest new entry.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QState& s, uint32_t n, uint32_t nb, uint32_t ws,
+                                                   bool first, uint32_t flag_id, uint32_t* pos0) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t i = lane; i < n; i += 32) {  // rank among the n new entries; the nb smallest are admitted
+    const float d = s.n_d[i];
+    const uint32_t id = s.n_id[i];
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < n; ++j) r += key_less(s.n_d[j], s.n_id[j], d, id) ? 1u : 0u;
+    if (r < nb) { s.s_d[r] = d; s.s_id[r] = id; }
+  }
+  __syncwarp();
+  if (first) {  // iter == 1 branch (:1636-1646): the worklist is the head of the sorted list
+    for (uint32_t i = lane; i < nb; i += 32) {
+      const uint32_t id = s.s_id[i];
+      s.w_d[i] = s.s_d[i];
+      s.w_id[i] = id;
+      s.w_v[i] = (id == a.medoid || id == flag_id) ? 1 : 0;
+    }
+    __syncwarp();
+    *pos0 = 0;
+    return nb;
+  }
+  const uint32_t newsize = min(ws + nb, a.L);
+  // new entries: position = index + lower_bound(W, d)  (new before old on ties); nb <= 65 -> at most 3 per lane
+  uint32_t npos[3];
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const uint32_t i = lane + 32 * e;
+    npos[e] = kNone;
+    if (i < nb) {
+      const float d = s.s_d[i];
+      uint32_t lo = 0, hi = ws;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (d <= s.w_d[mid]) hi = mid; else lo = mid + 1;
+      }
+      npos[e] = lo + i;
+    }
+  }
+  const uint32_t p0 = __shfl_sync(kFull, npos[0], 0);
+  __syncwarp();
+  for (int c = (int)((ws - 1) >> 5); c >= (int)(p0 >> 5); --c) {  // old entries at or after the insertion point, tail first
+    const uint32_t j = (uint32_t)c * 32 + lane;
+    const bool live = j < ws && j >= p0;
+    float d = 0.0f;
+    uint32_t id = 0, pos = kNone;
+    uint8_t v = 0;
+    if (live) {
+      d = s.w_d[j]; id = s.w_id[j]; v = s.w_v[j];
+      uint32_t lo = 0, hi = nb;
+      while (lo < hi) {  // upper_bound over the admitted new entries
+        const uint32_t mid = (lo + hi) >> 1;
+        if (d >= s.s_d[mid]) lo = mid + 1; else hi = mid;
+      }
+      pos = j + lo;
+    }
+    __syncwarp();
+    if (pos < newsize) { s.w_d[pos] = d; s.w_id[pos] = id; s.w_v[pos] = v; }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const uint32_t i = lane + 32 * e;
+    if (npos[e] < newsize) {
+      const uint32_t id = s.s_id[i];
+      s.w_d[npos[e]] = s.s_d[i];
+      s.w_id[npos[e]] = id;
+      s.w_v[npos[e]] = (id == flag_id) ? 1 : 0;
+    }
+  }
+  __syncwarp();
+  *pos0 = p0;
+  return newsize;
+}
+
+// ------------------------------------------------------------------------------------------------
 // stage 5: exact distances of the expanded nodes (compute_L2Dist, bang_search.cu:1254-1299) with
-// coalesced 16-byte loads, 8 lanes per row, two rows in flight per lane group; then the top-k by
-// (exact distance, id) (compute_NearestNeighbours, :1312-1368).
+// coalesced 16-byte loads, 8 lanes per row, two rows in flight per lane group; then the k smallest by
+// (exact distance, id) (compute_NearestNeighbours, :1312-1368) by k rounds of warp-wide min extraction.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
-  const uint32_t tid = threadIdx.x, t = tid & 7, slot = tid >> 3;
+  const uint32_t lane = threadIdx.x & 31, t = lane & 7, g = lane >> 3;
   float* cd = s.lut;  // the PQ table is dead by now
-  __syncthreads();
-  for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-    const uint32_t i0 = b0 + slot, i1 = b0 + 16 + slot;
+  __syncwarp();
+  for (uint32_t b0 = 0; b0 < n; b0 += 8) {
+    const uint32_t i0 = b0 + g, i1 = b0 + 4 + g;
     const uint32_t id0 = i0 < n ? s.cand_id[i0] : a.medoid, id1 = i1 < n ? s.cand_id[i1] : a.medoid;
-    const float d0 = l2_row_8lane<T>(row_ptr(a, id0) + kAdjBytes, s.q_f, a.vec_units, t);
-    const float d1 = l2_row_8lane<T>(row_ptr(a, id1) + kAdjBytes, s.q_f, a.vec_units, t);
+    float d0, d1;
+    l2_two_rows_8lane<T>(row_ptr(a, id0) + kAdjBytes, row_ptr(a, id1) + kAdjBytes, s.q_f, a.vec_units, t, &d0, &d1);
     if (t == 0 && i0 < n) cd[i0] = d0;
     if (t == 0 && i1 < n) cd[i1] = d1;
   }
-  __syncthreads();
-  for (uint32_t i = tid; i < n; i += kThreads) {
-    const float di = cd[i];
-    const uint32_t idi = s.cand_id[i];
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; ++j) rank += key_less(cd[j], s.cand_id[j], di, idi) ? 1u : 0u;
-    if (rank < a.k) {
-      a.out_ids[(size_t)q * a.k + rank] = idi;
-      a.out_dists[(size_t)q * a.k + rank] = di;
+  __syncwarp();
+  uint32_t last_d = 0, last_id = 0;
+  bool have_last = false;
+  for (uint32_t r = 0; r < a.k; ++r) {
+    uint32_t bd = 0xFFFFFFFFu, bid = kNone;
+    for (uint32_t i = lane; i < n; i += 32) {
+      const uint32_t db = __float_as_uint(cd[i]), id = s.cand_id[i];
+      const bool after = !have_last || db > last_d || (db == last_d && id > last_id);
+      if (after && (db < bd || (db == bd && id < bid))) { bd = db; bid = id; }
     }
-  }
-  for (uint32_t r = n + tid; r < a.k; r += kThreads) {
-    a.out_ids[(size_t)q * a.k + r] = 0xFFFFFFFFull;
-    a.out_dists[(size_t)q * a.k + r] = 3.402823466e+38f;
+    const uint32_t dmin = __reduce_min_sync(kFull, bd);
+    const uint32_t idmin = __reduce_min_sync(kFull, bd == dmin ? bid : kNone);
+    const bool found = idmin != kNone;
+    if (lane == 0) {
+      a.out_ids[(size_t)q * a.k + r] = found ? (uint64_t)idmin : 0xFFFFFFFFull;
+      a.out_dists[(size_t)q * a.k + r] = found ? __uint_as_float(dmin) : 3.402823466e+38f;
+    }
+    if (!found) { last_d = 0xFFFFFFFFu; last_id = kNone; }  // nothing left: the remaining ranks are filler too
+    else { last_d = dmin; last_id = idmin; }
+    have_last = true;
   }
 }
 
@@ -561,36 +606,34 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   QState s;
   carve<T>(s, smem_raw, MODE, a);
-  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = threadIdx.x;
   uint32_t* bloom = a.bloom + (size_t)blockIdx.x * kBloomWords;
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s.scal[S_QUERY] = atomicAdd(a.counter, 1u);
-    __syncthreads();
-    const uint32_t q = s.scal[S_QUERY];
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(a.counter, 1u);
+    q = __shfl_sync(kFull, q, 0);
     if (q >= a.Q) break;
 
     // ---- per-query setup: query -> smem, bloom filter cleared, PQ table built in place ----
-    uint32_t my_nb = fetch_adj(a, a.medoid);  // the first hop's adjacency row travels during the setup
+    uint2 my_nb = fetch_adj(a, a.medoid);  // the first hop's adjacency row travels during the setup
+    __syncwarp();
     load_query<T>(a, q, s.q_f);
     {
       uint4* b4 = reinterpret_cast<uint4*>(bloom);
-      for (uint32_t i = tid; i < kBloomWords / 4; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
+      for (uint32_t i = lane; i < kBloomWords / 4; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
     }
-    if (tid == 0) {
-      s.scal[S_CNT0] = 0; s.scal[S_CNT1] = 0; s.scal[S_SUMDEG] = 0; s.scal[S_NPASS] = 0; s.scal[S_POS0] = 0;
-      if (MODE != kExact) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
-    }
-    __syncthreads();
+    if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
+    __syncwarp();
     if (MODE != kExact) {
       build_pq_table(a, s.q_f, s.lut);
-      __syncthreads();
+      __syncwarp();
     }
+    __threadfence_block();  // the cleared filter is ordered before this query's tests and insertions
 
-    uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1;
+    uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1, sum_deg = 0, n_pass = 0, deg = 0, pos0 = 0;
     auto log_parent = [&](uint32_t node) {
-      if (tid == 0) {
+      if (lane == 0) {
         if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
         if (a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = node;
       }
@@ -599,33 +642,33 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
-      uint32_t par = 1;
-      uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, true, par);
-      Best b = scan_neighbours(s, par, n, a.medoid, true, 0.0f);
-      bool have = b.id != kNone;               // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
+      uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, true, &deg);
+      sum_deg += deg; n_pass += n;
+      Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
+      bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
       uint32_t parent = b.id, mark = have ? b.id : 0x01010101u;
       if (have) log_parent(parent);
       uint32_t pend_n = n, pend_nb = min(n, a.L), scan_from = 0;
       while (have || pend_n > 0) {
         if (have) my_nb = fetch_adj(a, parent);  // in flight during the merge
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
-          ws = merge_worklist(a, s, par, pend_n, pend_nb, ws, iter == 1, mark);
-          scan_from = min(scan_from, s.scal[S_POS0]);
+          ws = merge_worklist(a, s, pend_n, pend_nb, ws, iter == 1, mark, &pos0);
+          scan_from = min(scan_from, pos0);
         }
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
-        if (have) { par ^= 1u; n = expand<T, MODE>(a, s, bloom, my_nb, false, par); }  // `par` = buffer of the pending list
-        else n = 0u;
+        n = 0;
+        if (have) { n = expand<T, MODE>(a, s, bloom, my_nb, false, &deg); sum_deg += deg; n_pass += n; }
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
-        b = scan_neighbours(s, par, n, a.medoid, true, maxd);
+        b = scan_neighbours(s, n, a.medoid, true, maxd);
         const bool hasx = b.id != kNone;
         have = false;
         if (fu != kNone) {
           have = true;
           if (hasx && b.d < s.w_d[fu]) { parent = b.id; mark = b.id; }
-          else { parent = s.w_id[fu]; if (tid == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
+          else { parent = s.w_id[fu]; if (lane == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
         } else if (ws > 0 && hasx && b.d < maxd) {
           have = true; parent = b.id; mark = b.id;
         }
@@ -642,10 +685,10 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-        const uint32_t par = iter & 1u;
-        const uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, first, par);
+        const uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, first, &deg);
+        sum_deg += deg; n_pass += n;
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
-        const Best b = scan_neighbours(s, par, n, a.medoid, first, maxd);
+        const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
         uint32_t nb;
         bool have = false, from_new = false;
         if (first) {
@@ -659,22 +702,23 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
         }
         if (!have) break;  // nothing unvisited and nothing admitted: the merge would be a no-op
         uint32_t scan_from = fu == kNone ? ws : fu;
-        if (!from_new) { if (tid == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
+        if (!from_new) { if (lane == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
         log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
         const bool capped = iter == a.max_iter - 1;
         if (!capped) my_nb = fetch_adj(a, parent);  // in flight during the merge
         if (nb > 0) {
-          ws = merge_worklist(a, s, par, n, nb, ws, first, from_new ? parent : kNone);
-          scan_from = min(scan_from, s.scal[S_POS0]);
+          ws = merge_worklist(a, s, n, nb, ws, first, from_new ? parent : kNone, &pos0);
+          scan_from = min(scan_from, pos0);
         }
+        __syncwarp();
         fu = scan_unvisited(s, scan_from, ws);
         if (capped) break;
         ++iter;
       }
       if (MODE == kExact) {
         // top-k = head of the worklist (Exact parANN.cu:1273-1276)
-        __syncthreads();
-        for (uint32_t r = tid; r < a.k; r += kThreads) {
+        __syncwarp();
+        for (uint32_t r = lane; r < a.k; r += kThreads) {
           a.out_ids[(size_t)q * a.k + r] = r < ws ? (uint64_t)s.w_id[r] : 0xFFFFFFFFull;
           a.out_dists[(size_t)q * a.k + r] = r < ws ? s.w_d[r] : 3.402823466e+38f;
         }
@@ -682,26 +726,27 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
         rerank_and_write<T>(a, s, q, ncand);
       }
     }
-    if (tid == 0) {
+    if (lane == 0) {
       if (a.dump_ids) {
         a.dump_ids[(size_t)q * a.dump_stride] = a.medoid;
         a.dump_n[q] = min(ncand, a.dump_stride);
       }
       if (a.st_hops) a.st_hops[q] = ncand;
-      if (a.st_sumdeg) a.st_sumdeg[q] = s.scal[S_SUMDEG];
-      if (a.st_npass) a.st_npass[q] = s.scal[S_NPASS];
+      if (a.st_sumdeg) a.st_sumdeg[q] = sum_deg;
+      if (a.st_npass) a.st_npass[q] = n_pass;
     }
+    __syncwarp();
   }
 }
 
-// Standalone stage-1 kernel (parity test of populate_pqDist_par): one CTA per query, table to global.
+// Standalone stage-1 kernel (parity test of populate_pqDist_par): one warp per query, table to global.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) pq_table_kernel(const SearchArgs a, float* tables) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* q_f = reinterpret_cast<float*>(smem_raw);
   const uint32_t q = blockIdx.x;
   load_query<T>(a, q, q_f);
-  __syncthreads();
+  __syncwarp();
   build_pq_table(a, q_f, tables + (size_t)q * a.n_chunks * 256);
 }
 
