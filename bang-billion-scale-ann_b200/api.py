@@ -64,7 +64,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIB_CUDA
+    path = path or os.environ.get("BANG_B200_LIB") or _build.LIB_CUDA
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = ctypes.CDLL(path)

@@ -93,6 +93,8 @@ struct bang_b200_ctx {
   void* imported[kMaxShards] = {nullptr};
   uint8_t* d_codes = nullptr;
   float* d_pivT = nullptr;
+  float* d_piv = nullptr;
+  uint32_t chunk4 = 0;
   float* d_centroid = nullptr;
   uint32_t* d_chunk_off = nullptr;
   uint64_t device_bytes = 0;
@@ -106,12 +108,14 @@ struct bang_b200_ctx {
   uint32_t* d_bloom = nullptr;
   uint32_t* d_counter = nullptr;
   uint32_t *d_hops = nullptr, *d_sumdeg = nullptr, *d_npass = nullptr;
+  long long* d_phase = nullptr;
   float* h_dists = nullptr;  // pinned staging for the layout transpose
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int grid = 0, ctas_per_sm = 0, sm_count = 0;
+  int grid = 0, ctas_per_sm = 0, warps_per_cta = 0, sm_count = 0;
   size_t smem = 0;
   int lastQ = 0;
+  size_t bloom_bytes = 0, l2_persist_bytes = 0, l2_window_max = 0;
   bang_b200_timing_t timing = {};
 };
 
@@ -123,19 +127,19 @@ static size_t elem_size(int dtype) { return dtype == BANG_DT_FLOAT ? 4 : 1; }
 typedef void (*search_fn_t)(const SearchArgs);
 typedef void (*table_fn_t)(const SearchArgs, float*);
 
-template <typename T>
+template <typename T, bool C4>
 static search_fn_t pick_mode(int mode) {
   switch (mode) {
-    case BANG_MODE_BASE: return bang_search_kernel<T, kBase>;
-    case BANG_MODE_INMEMORY: return bang_search_kernel<T, kInmemory>;
-    default: return bang_search_kernel<T, kExact>;
+    case BANG_MODE_BASE: return bang_search_kernel<T, kBase, C4>;
+    case BANG_MODE_INMEMORY: return bang_search_kernel<T, kInmemory, C4>;
+    default: return bang_search_kernel<T, kExact, false>;
   }
 }
-static search_fn_t pick_kernel(int dtype, int mode) {
+static search_fn_t pick_kernel(int dtype, int mode, bool chunk4) {
   switch (dtype) {
-    case BANG_DT_FLOAT: return pick_mode<float>(mode);
-    case BANG_DT_INT8: return pick_mode<int8_t>(mode);
-    default: return pick_mode<uint8_t>(mode);
+    case BANG_DT_FLOAT: return chunk4 ? pick_mode<float, true>(mode) : pick_mode<float, false>(mode);
+    case BANG_DT_INT8: return chunk4 ? pick_mode<int8_t, true>(mode) : pick_mode<int8_t, false>(mode);
+    default: return chunk4 ? pick_mode<uint8_t, true>(mode) : pick_mode<uint8_t, false>(mode);
   }
 }
 static table_fn_t pick_table_kernel(int dtype) {
@@ -145,11 +149,11 @@ static table_fn_t pick_table_kernel(int dtype) {
     default: return pq_table_kernel<uint8_t>;
   }
 }
-static size_t smem_for(const bang_b200_ctx* c, uint32_t L, uint32_t cand_cap) {
+static LaunchGeom geometry_for(const bang_b200_ctx* c, uint32_t L, uint32_t cand_cap, size_t optin, size_t per_sm, int max_warps) {
   switch (c->dtype) {
-    case BANG_DT_FLOAT: return smem_bytes<float>(c->mode, c->n_chunks, c->vec_units, L, cand_cap);
-    case BANG_DT_INT8: return smem_bytes<int8_t>(c->mode, c->n_chunks, c->vec_units, L, cand_cap);
-    default: return smem_bytes<uint8_t>(c->mode, c->n_chunks, c->vec_units, L, cand_cap);
+    case BANG_DT_FLOAT: return launch_geometry<float>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps);
+    case BANG_DT_INT8: return launch_geometry<int8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps);
+    default: return launch_geometry<uint8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps);
   }
 }
 static uint32_t max_iter_for(int mode, int L) {
@@ -208,13 +212,18 @@ static int upload_pq(bang_b200_ctx* c, const PQHost& pq) {
   if (pq.chunk_off.back() != D) return set_err(BANG_E_FORMAT, "chunk offsets do not end at D");
   for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
     if (pq.chunk_off[i] > pq.chunk_off[i + 1]) return set_err(BANG_E_FORMAT, "chunk offsets not monotone");
+  c->chunk4 = (D % 4 == 0) ? 1u : 0u;
+  for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
+    if (pq.chunk_off[i] != 4 * i || pq.chunk_off[i + 1] != 4 * (i + 1)) c->chunk4 = 0;
+  CUDA_TRY(cudaMalloc(&c->d_piv, pq.pivots.size() * 4));
+  CUDA_TRY(cudaMemcpy(c->d_piv, pq.pivots.data(), pq.pivots.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&c->d_pivT, pivT.size() * 4));
   CUDA_TRY(cudaMalloc(&c->d_centroid, (size_t)D * 4));
   CUDA_TRY(cudaMalloc(&c->d_chunk_off, pq.chunk_off.size() * 4));
   CUDA_TRY(cudaMemcpy(c->d_pivT, pivT.data(), pivT.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->d_centroid, pq.centroid.data(), (size_t)D * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->d_chunk_off, pq.chunk_off.data(), pq.chunk_off.size() * 4, cudaMemcpyHostToDevice));
-  c->device_bytes += pivT.size() * 4 + (size_t)D * 4 + pq.chunk_off.size() * 4;
+  c->device_bytes += 2 * pivT.size() * 4 + (size_t)D * 4 + pq.chunk_off.size() * 4;
   return BANG_OK;
 }
 
@@ -373,8 +382,8 @@ extern "C" int bang_b200_unload(bang_handle_t c) {
   cudaSetDevice(c->device);
   for (int s = 0; s < kMaxShards; ++s)
     if (c->imported[s]) { cudaIpcCloseMemHandle(c->imported[s]); c->imported[s] = nullptr; }
-  cudaFree(c->d_rows); cudaFree(c->d_codes); cudaFree(c->d_pivT); cudaFree(c->d_centroid); cudaFree(c->d_chunk_off);
-  c->d_rows = nullptr; c->d_codes = nullptr; c->d_pivT = nullptr; c->d_centroid = nullptr; c->d_chunk_off = nullptr;
+  cudaFree(c->d_rows); cudaFree(c->d_codes); cudaFree(c->d_pivT); cudaFree(c->d_piv); cudaFree(c->d_centroid); cudaFree(c->d_chunk_off);
+  c->d_rows = nullptr; c->d_codes = nullptr; c->d_pivT = nullptr; c->d_piv = nullptr; c->d_centroid = nullptr; c->d_chunk_off = nullptr;
   c->loaded = false;
   c->device_bytes = 0;
   return BANG_OK;
@@ -445,26 +454,53 @@ extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
     if (!c->rows[s]) return set_err(BANG_E_STATE, "graph shard " + std::to_string(s) + " has not been imported");
   CUDA_TRY(cudaSetDevice(c->device));
   const uint32_t max_iter = max_iter_for(c->mode, c->L);
-  c->smem = smem_for(c, c->L, max_iter + 1);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode);
-  int max_optin = 0;
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4 != 0);
+  int max_optin = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  if (c->smem > (size_t)max_optin)
-    return set_err(BANG_E_UNSUPPORTED, "PQ table (" + std::to_string(c->n_chunks) + " chunks) + worklist need " +
-                                           std::to_string(c->smem) + " B of shared memory, device allows " + std::to_string(max_optin));
+  CUDA_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+  // Resident queries per SM: bounded by shared memory, and by default by the L2 share of their bloom
+  // filters (50 KB each, kept in L2: 16 x 148 x 50 KB = 118 MB).  BANG_B200_WARPS_PER_SM overrides.
+  int max_warps = 16;
+  if (const char* e = getenv("BANG_B200_WARPS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) max_warps = v; }
+  const LaunchGeom g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps);
+  if (g.warps_per_cta < 1)
+    return set_err(BANG_E_UNSUPPORTED, "pivot table (256 x " + std::to_string(c->D) + " floats) + one query's state do not fit in " +
+                                           std::to_string(max_optin) + " B of shared memory");
+  c->smem = g.smem;
+  c->warps_per_cta = g.warps_per_cta;
   CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, (const void*)fn, kThreads, c->smem));
-  if (c->ctas_per_sm < 1) return set_err(BANG_E_CUDA, "kernel does not fit on an SM");
-  c->grid = std::min(Q, c->ctas_per_sm * c->sm_count);
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, c->warps_per_cta * 32, c->smem));
+  if (occ < 1) return set_err(BANG_E_CUDA, "kernel does not fit on an SM");
+  c->ctas_per_sm = std::min(occ, g.ctas_per_sm);
+  c->grid = std::min((Q + c->warps_per_cta - 1) / c->warps_per_cta, c->ctas_per_sm * c->sm_count);
   const size_t qbytes = (size_t)Q * c->D * elem_size(c->dtype);
   CUDA_TRY(cudaMalloc(&c->d_queries, qbytes));
   CUDA_TRY(cudaMalloc(&c->d_ids, (size_t)Q * c->k * sizeof(uint64_t)));
   CUDA_TRY(cudaMalloc(&c->d_dists, (size_t)Q * c->k * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&c->d_bloom, (size_t)c->grid * kBloomWords * 4));
+  c->bloom_bytes = (size_t)c->grid * c->warps_per_cta * kBloomWords * 4;
+  CUDA_TRY(cudaMalloc(&c->d_bloom, c->bloom_bytes));
+  {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    c->l2_persist_bytes = 0;
+    c->l2_window_max = (size_t)max_window;
+    if (max_persist > 0 && max_window > 0 && !getenv("BANG_B200_NO_L2_PERSIST")) {
+      size_t want = std::min((size_t)max_persist, c->bloom_bytes);
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2_persist_bytes = want;
+    }
+    if (getenv("BANG_B200_VERBOSE"))
+      fprintf(stderr, "[bang_b200] bloom %zu MiB, L2 persisting max %d MiB window max %d MiB -> persisting %zu MiB\n",
+              c->bloom_bytes >> 20, max_persist >> 20, max_window >> 20, c->l2_persist_bytes >> 20);
+  }
   CUDA_TRY(cudaMalloc(&c->d_counter, 4));
   CUDA_TRY(cudaMalloc(&c->d_hops, (size_t)Q * 4));
   CUDA_TRY(cudaMalloc(&c->d_sumdeg, (size_t)Q * 4));
   CUDA_TRY(cudaMalloc(&c->d_npass, (size_t)Q * 4));
+#ifdef BANG_PHASE_TIMERS
+  CUDA_TRY(cudaMalloc(&c->d_phase, (size_t)Q * PT_COUNT * 8));
+#endif
   CUDA_TRY(cudaMallocHost(&c->h_dists, (size_t)Q * c->k * sizeof(float)));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&c->ev0));
@@ -489,7 +525,7 @@ extern "C" int bang_b200_free(bang_handle_t c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_queries); cudaFree(c->d_ids); cudaFree(c->d_dists); cudaFree(c->d_bloom); cudaFree(c->d_counter);
-  cudaFree(c->d_hops); cudaFree(c->d_sumdeg); cudaFree(c->d_npass);
+  cudaFree(c->d_hops); cudaFree(c->d_sumdeg); cudaFree(c->d_npass); cudaFree(c->d_phase); c->d_phase = nullptr;
   cudaFreeHost(c->h_dists);
   cudaStreamDestroy(c->stream);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -503,6 +539,20 @@ extern "C" int bang_b200_free(bang_handle_t c) {
 // ------------------------------------------------------------------------------------------------
 // query
 // ------------------------------------------------------------------------------------------------
+// The bloom filters are the only data re-read during a search: pin them in the persisting part of L2
+// (cudaAccessPolicyWindow) so the one-touch gathers of rows and codes cannot evict them.
+static void apply_l2_window(const bang_b200_ctx* c, cudaStream_t st) {
+  if (!c->l2_persist_bytes || !c->d_bloom) return;
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.base_ptr = c->d_bloom;
+  v.accessPolicyWindow.num_bytes = std::min(c->bloom_bytes, c->l2_window_max);
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_bytes / (double)std::max<size_t>(1, v.accessPolicyWindow.num_bytes));
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists) {
   memset(a, 0, sizeof(*a));
   for (int s = 0; s < kMaxShards; ++s) a->rows[s] = c->rows[s];
@@ -512,6 +562,8 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   a->code_stride = c->code_stride;
   a->n_chunks = c->n_chunks;
   a->pivT = c->d_pivT;
+  a->piv = c->d_piv;
+  a->chunk4 = c->chunk4;
   a->centroid = c->d_centroid;
   a->chunk_off = c->d_chunk_off;
   a->D = c->D;
@@ -531,20 +583,22 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   a->st_hops = c->d_hops;
   a->st_sumdeg = c->d_sumdeg;
   a->st_npass = c->d_npass;
+  a->st_phase = c->d_phase;
 }
 
 static int launch_search(bang_b200_ctx* c, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists, cudaStream_t st) {
   SearchArgs a;
   fill_args(c, &a, d_queries, Q, d_ids, d_dists);
+  apply_l2_window(c, st);
   CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4, st));
-  const int grid = std::min(Q, c->grid);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode);
-  fn<<<grid, kThreads, c->smem, st>>>(a);
+  const int grid = std::min((Q + c->warps_per_cta - 1) / c->warps_per_cta, c->grid);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4 != 0);
+  fn<<<grid, c->warps_per_cta * 32, c->smem, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->lastQ = Q;
   c->timing.launches = 1;
   c->timing.grid = grid;
-  c->timing.block = kThreads;
+  c->timing.block = c->warps_per_cta * 32;
   c->timing.smem_bytes = (uint32_t)c->smem;
   c->timing.ctas_per_sm = c->ctas_per_sm;
   return BANG_OK;
@@ -642,12 +696,21 @@ extern "C" int bang_b200_pq_table(bang_handle_t c, const void* queries, int Q, f
   const size_t smem = (size_t)c->vec_units * 16 * (c->dtype == BANG_DT_FLOAT ? 1 : 4);
   e = cudaMemcpy(d_q, queries, qbytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    pick_table_kernel(c->dtype)<<<Q, kThreads, smem>>>(a, d_t);
+    pick_table_kernel(c->dtype)<<<Q, 32, smem>>>(a, d_t);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(tables, d_t, tbytes, cudaMemcpyDeviceToHost);
   cudaFree(d_q);
   cudaFree(d_t);
   if (e != cudaSuccess) return set_err(BANG_E_CUDA, std::string("pq_table: ") + cudaGetErrorString(e));
+  return BANG_OK;
+}
+
+// Debug builds only (-DBANG_PHASE_TIMERS): per-query, per-phase SM clock totals of the last query call.
+extern "C" int bang_b200_debug_phase_clocks(bang_handle_t c, long long* out /*[Q][16]*/) {
+  if (!c || !out) return set_err(BANG_E_ARG, "null argument");
+  if (!c->d_phase) return set_err(BANG_E_UNSUPPORTED, "library built without BANG_PHASE_TIMERS");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, c->d_phase, (size_t)c->lastQ * PT_COUNT * 8, cudaMemcpyDeviceToHost));
   return BANG_OK;
 }

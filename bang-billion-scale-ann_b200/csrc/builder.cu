@@ -286,12 +286,19 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
   if (max_batch == 0) max_batch = (uint32_t)std::max<uint64_t>(1024, std::min<uint64_t>(N / 50, 65536));
   const uint32_t MB = max_batch;
   // search scratch
-  auto kern = bang_search_kernel<T, kExact>;
-  const size_t smem = smem_bytes<T>(kExact, 0, vec_units, L, cand_cap);
+  auto kern = bang_search_kernel<T, kExact, false>;
+  int max_optin = 0, per_sm = 0;
+  B_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  B_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+  const LaunchGeom geom = launch_geometry<T>(kExact, D, 0, vec_units, L, cand_cap, (size_t)max_optin, (size_t)per_sm, 16);
+  if (geom.warps_per_cta < 1) { b_err = "vector too large for the search kernel's shared memory"; return BANG_E_UNSUPPORTED; }
+  const size_t smem = geom.smem;
+  const int wpc = geom.warps_per_cta;
   B_TRY(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas = 0;
-  B_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, (const void*)kern, kThreads, smem));
-  const int grid_max = std::max(1, ctas * sms);
+  B_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, (const void*)kern, wpc * 32, smem));
+  ctas = std::max(1, std::min(ctas, geom.ctas_per_sm));
+  const int grid_max = ctas * sms;
   uint8_t* d_q = nullptr; uint64_t* d_ids = nullptr; float* d_dd = nullptr; uint32_t *d_bloom = nullptr, *d_counter = nullptr;
   uint32_t *d_dump = nullptr, *d_dump_n = nullptr, *d_dst = nullptr, *d_src = nullptr, *d_dst2 = nullptr, *d_src2 = nullptr;
   uint32_t *d_seg = nullptr, *d_segc = nullptr;
@@ -299,7 +306,7 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
   B_TRY(cudaMalloc(&d_q, (size_t)MB * vec_bytes));
   B_TRY(cudaMalloc(&d_ids, (size_t)MB * 8));
   B_TRY(cudaMalloc(&d_dd, (size_t)MB * 4));
-  B_TRY(cudaMalloc(&d_bloom, (size_t)grid_max * kBloomWords * 4));
+  B_TRY(cudaMalloc(&d_bloom, (size_t)grid_max * wpc * kBloomWords * 4));
   B_TRY(cudaMalloc(&d_counter, 4));
   B_TRY(cudaMalloc(&d_dump, (size_t)MB * cand_cap * 4));
   B_TRY(cudaMalloc(&d_dump_n, (size_t)MB * 4));
@@ -329,7 +336,7 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
     gather_queries_kernel<<<(unsigned)(((size_t)B * vec_bytes + 255) / 256), 256>>>((const uint8_t*)d_vectors, vec_bytes, ids, B, d_q);
     B_TRY(cudaMemsetAsync(d_counter, 0, 4));
     a.Q = B;
-    kern<<<std::min<int>(B, grid_max), kThreads, smem>>>(a);
+    kern<<<std::min<int>((B + wpc - 1) / wpc, grid_max), wpc * 32, smem>>>(a);
     prune_batch_kernel<T><<<B, kPruneThreads, prune_smem>>>(rows, row_stride, vec_units, ids, B, d_dump, d_dump_n, cand_cap, alpha);
     const uint32_t np = B * kMaxR;
     emit_reverse_kernel<<<(np + 255) / 256, 256>>>(rows, row_stride, ids, B, d_dst, d_src);

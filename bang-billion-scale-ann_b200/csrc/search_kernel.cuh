@@ -8,12 +8,16 @@
 // 2 memsets, up to 5 PCIe copies and 3 stream syncs per hop (bang_search.cu:701-958) is one launch here;
 // the LUT, worklist, candidate log and neighbour lists never leave shared memory.
 //
-// Why one warp: the search is a dependent pointer chase whose per-hop work is tiny (64 hashes, ~10 PQ
-// distances, a 150-entry merge).  Residency is capped by the 32 KB fp32 LUT per query (6 queries per
-// SM), so the lever is the per-hop critical path, not occupancy.  ncu on the 4-warp versions
-// (profiles/r1a, r1b) showed 22-40 % of the samples in CTA barriers and 586 instructions per warp-hop,
-// mostly redundant; a single warp needs no CTA barrier (only __syncwarp), reduces with redux.sync, and
-// leaves the issue slots to the other five queries of the SM.  Per hop:
+// Why one warp per query and no per-query LUT: the search is a dependent pointer chase whose per-hop
+// work is tiny (64 hashes, ~10 PQ distances, a 150-entry merge), so throughput = resident queries /
+// per-hop latency.  Measured on B200 (profiles/r1_*): time per 10k-query batch falls almost linearly with
+// the number of resident queries per SM, and the reference's per-query fp32 table (32 KB at m = 32) caps
+// residency at 6.  A table entry is a pure function of (query, chunk, code): tbl[c][k] = the fmaf chain
+// over the chunk's dimensions.  Evaluating that same chain on demand from ONE pivot table shared by all
+// the warps of the CTA (128 KB of shared memory at D = 128) gives bit-identical distances and leaves
+// ~4 KB of private state per query, i.e. 16-20 resident queries per SM.  CTA barriers are used once (to
+// publish the pivot table); afterwards every warp runs on its own with __syncwarp and redux.sync.
+// Per hop:
 //   * the adjacency row (256 B) was requested at the end of the previous hop, one 8-byte load per lane;
 //   * visited filter with snapshot semantics: 4 bloom words per lane in one L2 round trip, insertion
 //     by fire-and-forget `red.or` (nothing waits on it);
@@ -37,7 +41,8 @@
 
 namespace bang {
 
-constexpr int kThreads = 32;            // one warp per query (see the header comment)
+constexpr int kThreads = 32;            // threads per query = one warp (see the header comment)
+constexpr int kMaxWarpsPerCta = 16;  // 512 threads: up to 128 registers per thread
 constexpr int kMaxR = 64;               // MAX_R, bang_search.cu:35
 constexpr int kListCap = kMaxR + 8;     // medoid + R neighbours, padded
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
@@ -57,7 +62,9 @@ struct SearchArgs {
   const uint8_t* codes;     // [N][code_stride], bytes permuted per 32-chunk group (see repack_codes)
   uint32_t code_stride;
   uint32_t n_chunks;
-  const float* pivT;        // [D][256]   pivots transposed as the reference does at load (:281-285)
+  const float* pivT;        // [D][256]   pivots transposed as the reference does at load (:281-285); stage-1 kernel only
+  const float* piv;         // [256][D]   pivots in file order: the shared-memory table of the search kernel
+  uint32_t chunk4;          // 1 when every chunk spans exactly 4 dimensions (fast 16-byte path)
   const float* centroid;    // [D]
   const uint32_t* chunk_off;  // [n_chunks+1]
   uint32_t D;               // dims of the index
@@ -80,6 +87,7 @@ struct SearchArgs {
   uint32_t* dump_ids;
   uint32_t* dump_n;
   uint32_t dump_stride;
+  long long* st_phase;      // debug builds (-DBANG_PHASE_TIMERS): [Q][16] per-phase SM clocks, else null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -150,16 +158,39 @@ __device__ __forceinline__ const uint8_t* row_ptr(const SearchArgs& a, uint32_t 
   return a.rows[s] + (size_t)(id / a.n_shards) * a.row_stride;  // local HBM or a peer mapping over NVLink
 }
 
+// L2 residency control.  The per-query bloom filters (50 KB each, re-read every hop) are the only data
+// with reuse; graph rows and PQ codes are touched once per query.  Streaming loads therefore carry an
+// evict-first L2 policy and bypass L1, bloom accesses an evict-last policy, so the gathers do not push the
+// filters out of the 126 MB L2 (ncu: profiles/r1_*: DRAM bytes vs algorithmic bytes).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(l2_policy_evict_first()));
   return r;
 }
 __device__ __forceinline__ uint32_t ld_nc_u32(const void* p) {
   uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_evict_first()));
   return r;
+}
+// bloom word: coherent at L2 (skips L1), kept with evict-last priority
+__device__ __forceinline__ uint32_t bloom_ld(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_evict_last()));
+  return r;
+}
+__device__ __forceinline__ void bloom_or(uint32_t* p, uint32_t bit) {
+  asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(bit), "l"(l2_policy_evict_last()) : "memory");
 }
 
 // Exact squared L2 between one HBM row vector and the query (fp32 copy in shared memory).
@@ -214,15 +245,17 @@ __device__ __forceinline__ void l2_two_rows_8lane(const uint8_t* va, const uint8
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory state of one query
+// shared memory: one CTA-wide read-only region (pivot table, chunk offsets) + one private region per warp
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct QState {
+  const float* piv_s;       // [256][D] pivots (CTA-shared, PQ modes)
+  const uint32_t* coff_s;   // [n_chunks+1] chunk offsets (CTA-shared, PQ modes)
   float* q_f;        // [vec_units * E] query as fp32, zero padded
-  float* lut;        // [n_chunks][256] (PQ modes); re-used for the candidates' exact distances in stage 5
-  float* w_d;        // worklist [w_cap], sorted by distance
+  float* qc;         // [D] query - centroid (PQ modes)
+  float* w_d;        // worklist [w_cap], sorted by distance; the exact distances of stage 5 re-use this block
   uint32_t* w_id;
   uint8_t* w_v;      // visited flags
   uint32_t* n_id;    // [kListCap] filtered neighbours of this hop, unordered
@@ -234,28 +267,32 @@ struct QState {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t lut_region_bytes(int mode, uint32_t n_chunks, uint32_t cand_cap) {
+// CTA-shared bytes
+__host__ __device__ inline size_t cta_shared_bytes(int mode, uint32_t D, uint32_t n_chunks) {
   if (mode == kExact) return 0;
-  const size_t lut = (size_t)n_chunks * 256 * 4, cd = align_up((size_t)cand_cap * 4, 16);
-  return lut > cd ? lut : cd;
+  return align_up((size_t)256 * D * 4, 16) + align_up((size_t)(n_chunks + 1) * 4, 16);
 }
-
+// private bytes per warp (= per resident query)
 template <typename T>
-__host__ __device__ inline size_t smem_bytes(int mode, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap) {
+__host__ __device__ inline size_t warp_private_bytes(int mode, uint32_t D, uint32_t vec_units, uint32_t L, uint32_t cand_cap) {
   size_t b = 0;
-  b += align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);
-  b += lut_region_bytes(mode, n_chunks, cand_cap);
-  b += align_up(L, 16) * 9;            // worklist: dist + id + visited
-  b += (size_t)kListCap * 4 * 4;       // neighbour list + sorted admitted list
-  if (mode != kExact) b += align_up((size_t)cand_cap * 4, 16);
+  b += align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);   // q_f
+  if (mode != kExact) b += align_up((size_t)D * 4, 16);            // qc
+  b += align_up(L, 16) * 9;                                         // worklist: dist + id + visited
+  b += (size_t)kListCap * 4 * 4;                                    // neighbour list + sorted admitted list
+  if (mode != kExact) b += align_up((size_t)cand_cap * 4, 16);      // candidate log
   return align_up(b, 16);
 }
 
 template <typename T>
-__device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const SearchArgs& a) {
+__device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const SearchArgs& a, uint32_t warp) {
   size_t o = 0;
+  s.piv_s = (const float*)(base + o);
+  s.coff_s = (const uint32_t*)(base + align_up((size_t)256 * a.D * 4, 16));
+  o += cta_shared_bytes(mode, a.D, a.n_chunks);
+  o += (size_t)warp * warp_private_bytes<T>(mode, a.D, a.vec_units, a.L, a.cand_cap);
   s.q_f = (float*)(base + o); o += align_up((size_t)a.vec_units * Elem<T>::kPerUnit * 4, 16);
-  s.lut = (float*)(base + o); o += lut_region_bytes(mode, a.n_chunks, a.cand_cap);
+  s.qc = (float*)(base + o); if (mode != kExact) o += align_up((size_t)a.D * 4, 16);
   const size_t wcap = align_up(a.L, 16);
   s.w_d = (float*)(base + o); o += wcap * 4;
   s.w_id = (uint32_t*)(base + o); o += wcap * 4;
@@ -268,10 +305,10 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// stage 1: per-query PQ distance table into shared memory (or global for the standalone kernel)
+// stage 1 (standalone kernel only): the reference's per-query PQ distance table, written to global.
 // tbl[c][k] = sum_{j in chunk c} (pivT[j][k] - (q[j] - centroid[j]))^2, j ascending, fmaf
-// (populate_pqDist_par, bang_search.cu:1118-1129).  Lane l owns centres 4l..4l+3 and 128+4l..128+4l+3:
-// two coalesced 512-byte requests per dimension, 8 independent accumulators per lane.
+// (populate_pqDist_par, bang_search.cu:1118-1129).  The search kernel does not materialise the table:
+// adc_entry() below evaluates the same chain on demand.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void build_pq_table(const SearchArgs& a, const float* q_f, float* tbl /*[m][256]*/) {
   const uint32_t lane = threadIdx.x & 31;
@@ -295,20 +332,72 @@ __device__ __forceinline__ void build_pq_table(const SearchArgs& a, const float*
   }
 }
 
+// One table entry on demand: the identical operation sequence as build_pq_table for (chunk c, centre `code`),
+// reading the pivot row from the CTA-shared table — hence bit-identical to the reference's tbl[c][code].
+template <bool CHUNK4>
+__device__ __forceinline__ float adc_entry(const QState& s, uint32_t D, uint32_t c, uint32_t code) {
+  const float* p = s.piv_s + (size_t)code * D;
+  float acc = 0.0f;
+  if (CHUNK4) {
+    const float4 pv = *reinterpret_cast<const float4*>(p + 4 * c);
+    const float4 qv = *reinterpret_cast<const float4*>(s.qc + 4 * c);
+    float d;
+    d = __fsub_rn(pv.x, qv.x); acc = __fmaf_rn(d, d, acc);
+    d = __fsub_rn(pv.y, qv.y); acc = __fmaf_rn(d, d, acc);
+    d = __fsub_rn(pv.z, qv.z); acc = __fmaf_rn(d, d, acc);
+    d = __fsub_rn(pv.w, qv.w); acc = __fmaf_rn(d, d, acc);
+  } else {
+    const uint32_t j0 = s.coff_s[c], j1 = s.coff_s[c + 1];
+    for (uint32_t j = j0; j < j1; ++j) { const float d = __fsub_rn(p[j], s.qc[j]); acc = __fmaf_rn(d, d, acc); }
+  }
+  return acc;
+}
+
+// partial ADC sum of one 32-chunk group for lane t: chunks base+t, base+t+8, base+t+16, base+t+24 (ascending)
+template <bool CHUNK4>
+__device__ __forceinline__ float adc_group(const QState& s, const SearchArgs& a, uint32_t word, uint32_t base, uint32_t t, float sum) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const uint32_t c = base + t + 8 * b;
+    if (c < a.n_chunks) sum = __fadd_rn(sum, adc_entry<CHUNK4>(s, a.D, c, (word >> (8 * b)) & 0xff));
+  }
+  return sum;
+}
+
 template <typename T>
 __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, float* q_f) {
   const T* src = reinterpret_cast<const T*>(a.queries) + (size_t)q * a.q_dim;
   const uint32_t n = a.vec_units * Elem<T>::kPerUnit;
-  for (uint32_t i = threadIdx.x; i < n; i += kThreads) q_f[i] = i < a.q_dim ? (float)src[i] : 0.0f;
+  for (uint32_t i = threadIdx.x & 31; i < n; i += 32) q_f[i] = i < a.q_dim ? (float)src[i] : 0.0f;
 }
 
 // adjacency prefetch: lane l requests neighbour slots 2l and 2l+1 of `node`'s HBM row (one 256-byte request)
 __device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node) {
   uint2 r;
   const uint8_t* p = row_ptr(a, node) + 8 * (threadIdx.x & 31);
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+               : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(l2_policy_evict_first()));
   return r;
 }
+
+// Debug-only phase timers (-DBANG_PHASE_TIMERS): every lane keeps SM-clock deltas per phase; lane 0's are
+// written per query to SearchArgs::st_phase[q][16].  Compiled out of the product build (empty struct).
+enum { PT_SETUP = 0, PT_ADJWAIT, PT_HASH, PT_BLOOM, PT_COMPACT, PT_CODEWAIT, PT_LUT, PT_SCAN, PT_DECIDE, PT_MERGE, PT_UNVIS,
+       PT_RERANK, PT_TOPK, PT_HOPS, PT_MERGES, PT_COUNT = 16 };
+#ifdef BANG_PHASE_TIMERS
+struct Prof {
+  long long t, acc[PT_COUNT];
+  __device__ __forceinline__ void start() { for (int i = 0; i < PT_COUNT; ++i) acc[i] = 0; t = clock64(); }
+  __device__ __forceinline__ void tick(int i) { const long long n = clock64(); acc[i] += n - t; t = n; }
+  __device__ __forceinline__ void count(int i) { acc[i] += 1; }
+};
+#else
+struct Prof {
+  __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void tick(int) {}
+  __device__ __forceinline__ void count(int) {}
+};
+#endif
 
 struct BloomPos { uint32_t w1, b1, w2, b2; };
 template <int MODE>
@@ -333,31 +422,43 @@ __device__ __forceinline__ BloomPos bloom_pos(uint32_t id) {
 //   exact    compute_neighborDist_par                 BANG_Exactdistance/parANN.cu:1139-1179
 // Returns the number of accepted candidates; n_id/n_d hold them unordered; *deg_out = degree of the node.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE>
+template <typename T, int MODE, bool CHUNK4>
 __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint32_t* bloom, uint2 nb2, bool first,
-                                           uint32_t* deg_out) {
+                                           uint32_t* deg_out, Prof& pf) {
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
   const uint32_t id0 = nb2.x, id1 = nb2.y;
   const bool v0 = id0 != kNoNbr, v1 = id1 != kNoNbr;
+#ifdef BANG_PHASE_TIMERS
+  if (__any_sync(kFull, id0 == 0x12345678u && id1 == 0x9abcdef0u)) printf("");  // forces the adjacency load to complete here
+  pf.tick(PT_ADJWAIT);
+#endif
   const BloomPos p0 = bloom_pos<MODE>(id0), p1 = bloom_pos<MODE>(id1);
+#ifdef BANG_PHASE_TIMERS
+  if (__any_sync(kFull, p0.w1 == 0xFFFFFFFFu)) printf("");
+  pf.tick(PT_HASH);
+#endif
   bool acc0 = v0, acc1 = v1;
   if (!first) {
     uint32_t x01 = 0, x02 = 0, x11 = 0, x12 = 0;
-    if (v0) { x01 = __ldcg(bloom + p0.w1); if (MODE != kExact) x02 = __ldcg(bloom + p0.w2); }
-    if (v1) { x11 = __ldcg(bloom + p1.w1); if (MODE != kExact) x12 = __ldcg(bloom + p1.w2); }
+    if (v0) { x01 = bloom_ld(bloom + p0.w1); if (MODE != kExact) x02 = bloom_ld(bloom + p0.w2); }
+    if (v1) { x11 = bloom_ld(bloom + p1.w1); if (MODE != kExact) x12 = bloom_ld(bloom + p1.w2); }
     if (MODE == kExact) { acc0 = v0 && !(x01 & p0.b1); acc1 = v1 && !(x11 & p1.b1); }
     else { acc0 = v0 && !((x01 & p0.b1) && (x02 & p0.b2)); acc1 = v1 && !((x11 & p1.b1) && (x12 & p1.b2)); }
   }
   __syncwarp();  // every test precedes every insertion
-  if (acc0) { atomicOr(bloom + p0.w1, p0.b1); if (MODE != kExact) atomicOr(bloom + p0.w2, p0.b2); }  // RED.OR: results unused
-  if (acc1) { atomicOr(bloom + p1.w1, p1.b1); if (MODE != kExact) atomicOr(bloom + p1.w2, p1.b2); }
+#ifdef BANG_PHASE_TIMERS
+  if (__any_sync(kFull, acc0 && id0 == 0x12345678u)) printf("");
+  pf.tick(PT_BLOOM);
+#endif
+  if (acc0) { bloom_or(bloom + p0.w1, p0.b1); if (MODE != kExact) bloom_or(bloom + p0.w2, p0.b2); }  // fire and forget
+  if (acc1) { bloom_or(bloom + p1.w1, p1.b1); if (MODE != kExact) bloom_or(bloom + p1.w2, p1.b2); }
   uint32_t pre = 0;
   if (first) {
     pre = 1;
     if (lane == 0) {
       const BloomPos pm = bloom_pos<MODE>(a.medoid);
-      atomicOr(bloom + pm.w1, pm.b1);
-      if (MODE != kExact) atomicOr(bloom + pm.w2, pm.b2);
+      bloom_or(bloom + pm.w1, pm.b1);
+      if (MODE != kExact) bloom_or(bloom + pm.w2, pm.b2);
       s.n_id[0] = a.medoid;
     }
   }
@@ -368,6 +469,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   if (acc1) s.n_id[pre + c0 + __popc(m1 & lt)] = id1;
   *deg_out = __popc(__ballot_sync(kFull, v0)) + __popc(__ballot_sync(kFull, v1));
   __syncwarp();
+  pf.tick(PT_COMPACT);
   const uint32_t t = lane & 7, g = lane >> 3;  // 4 candidates per pass
   if (MODE == kExact) {
     for (uint32_t k0 = 0; k0 < n; k0 += 8) {  // two rows in flight per lane group
@@ -387,17 +489,15 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
         w[p] = 0;
         if (k < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[k] * a.code_stride + 4 * t);
       }
+#ifdef BANG_PHASE_TIMERS
+      if (__any_sync(kFull, (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x12345678u)) printf("");
+      pf.tick(PT_CODEWAIT);
+#endif
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         if (k0 + p * 4 < n) {  // warp-uniform
           const uint32_t k = k0 + p * 4 + g;
-          float sum = 0.0f;
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const uint32_t c = t + 8 * b;
-            if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((w[p] >> (8 * b)) & 0xff)]);
-          }
-          sum = tree8(sum);
+          const float sum = tree8(adc_group<CHUNK4>(s, a, w[p], 0, t, 0.0f));
           if (t == 0 && k < n) s.n_d[k] = sum;
         }
       }
@@ -411,22 +511,15 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       for (uint32_t gg = 0; gg < groups; gg += 2) {
         const uint32_t wa = ld_nc_u32(row + gg * 32);
         const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32) : 0u;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t c = gg * 32 + t + 8 * b;
-          if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((wa >> (8 * b)) & 0xff)]);
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t c = (gg + 1) * 32 + t + 8 * b;
-          if (c < a.n_chunks) sum = __fadd_rn(sum, s.lut[c * 256 + ((wb >> (8 * b)) & 0xff)]);
-        }
+        sum = adc_group<CHUNK4>(s, a, wa, gg * 32, t, sum);
+        sum = adc_group<CHUNK4>(s, a, wb, (gg + 1) * 32, t, sum);
       }
       sum = tree8(sum);
       if (t == 0 && k < n) s.n_d[k] = sum;
     }
   }
   __syncwarp();
+  pf.tick(PT_LUT);
   return n;
 }
 
@@ -472,6 +565,42 @@ __device__ __forceinline__ uint32_t admit_count(uint32_t below, uint32_t n, uint
   return max(min(below, min(L, n)), min(L - ws, n));
 }
 
+// The nb admitted entries (the nb smallest of the n new ones by (dist, id)), sorted, into s_id/s_d.
+// Common case (worklist full): the admitted set is exactly the entries closer than the current tail, a
+// handful per hop — compacted with ballots and ranked through shuffles.  Otherwise: rank among all n.
+__device__ __forceinline__ void select_admitted(const QState& s, uint32_t n, uint32_t nb, uint32_t below, float maxd) {
+  const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+  if (nb == below && nb <= 32) {
+    uint32_t base = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      const bool in = i < n && s.n_d[i] < maxd;
+      const uint32_t m = __ballot_sync(kFull, in);
+      if (in) { const uint32_t p = base + __popc(m & lt); s.s_d[p] = s.n_d[i]; s.s_id[p] = s.n_id[i]; }
+      base += __popc(m);
+    }
+    __syncwarp();
+    uint32_t kd = 0xFFFFFFFFu, ki = kNone;
+    if (lane < nb) { kd = __float_as_uint(s.s_d[lane]); ki = s.s_id[lane]; }
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < nb; ++j) {
+      const uint32_t od = __shfl_sync(kFull, kd, j), oi = __shfl_sync(kFull, ki, j);
+      r += (od < kd || (od == kd && oi < ki)) ? 1u : 0u;
+    }
+    __syncwarp();
+    if (lane < nb) { s.s_d[r] = __uint_as_float(kd); s.s_id[r] = ki; }
+  } else {
+    for (uint32_t i = lane; i < n; i += 32) {
+      const float d = s.n_d[i];
+      const uint32_t id = s.n_id[i];
+      uint32_t r = 0;
+      for (uint32_t j = 0; j < n; ++j) r += key_less(s.n_d[j], s.n_id[j], d, id) ? 1u : 0u;
+      if (r < nb) { s.s_d[r] = d; s.s_id[r] = id; }
+    }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // stage 4b: (dist, id) sort of the new neighbours + merge into the worklist, in place.
 // compute_BestLSets_par_sort_msort + compute_BestLSets_par_merge (bang_search.cu:1533-1585, 1605-1715):
@@ -482,17 +611,10 @@ __device__ __forceinline__ uint32_t admit_count(uint32_t below, uint32_t n, uint
 // only from the first insertion point on, so nothing is overwritten before it is read.
 // Returns the new size; *pos0 = position of the closest new entry.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QState& s, uint32_t n, uint32_t nb, uint32_t ws,
-                                                   bool first, uint32_t flag_id, uint32_t* pos0) {
+__device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QState& s, uint32_t n, uint32_t nb, uint32_t below,
+                                                   float maxd, uint32_t ws, bool first, uint32_t flag_id, uint32_t* pos0) {
   const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t i = lane; i < n; i += 32) {  // rank among the n new entries; the nb smallest are admitted
-    const float d = s.n_d[i];
-    const uint32_t id = s.n_id[i];
-    uint32_t r = 0;
-    for (uint32_t j = 0; j < n; ++j) r += key_less(s.n_d[j], s.n_id[j], d, id) ? 1u : 0u;
-    if (r < nb) { s.s_d[r] = d; s.s_id[r] = id; }
-  }
-  __syncwarp();
+  select_admitted(s, n, nb, first ? kNone : below, maxd);
   if (first) {  // iter == 1 branch (:1636-1646): the worklist is the head of the sorted list
     for (uint32_t i = lane; i < nb; i += 32) {
       const uint32_t id = s.s_id[i];
@@ -565,7 +687,7 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
 template <typename T>
 __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31, t = lane & 7, g = lane >> 3;
-  float* cd = s.lut;  // the PQ table is dead by now
+  float* cd = s.w_d;  // the worklist block is dead by now; cand_cap floats fit in it (see warp_private_bytes)
   __syncwarp();
   for (uint32_t b0 = 0; b0 < n; b0 += 8) {
     const uint32_t i0 = b0 + g, i1 = b0 + 4 + g;
@@ -599,15 +721,25 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: blockDim.x = 32 * (query warps per CTA)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs a) {
+template <typename T, int MODE, bool CHUNK4>
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  if (MODE != kExact) {
+    // the pivot table and the chunk offsets, once per CTA, shared by all its query warps
+    float4* dst = reinterpret_cast<float4*>(smem_raw);
+    const float4* src = reinterpret_cast<const float4*>(a.piv);
+    const uint32_t n4 = 256u * a.D / 4u;  // D*256 floats; 256*D*4 bytes is a multiple of 16
+    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+    uint32_t* coff = reinterpret_cast<uint32_t*>(smem_raw + align_up((size_t)256 * a.D * 4, 16));
+    for (uint32_t i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) coff[i] = a.chunk_off[i];
+    __syncthreads();  // the only CTA barrier; from here on the warps never meet again
+  }
   QState s;
-  carve<T>(s, smem_raw, MODE, a);
-  const uint32_t lane = threadIdx.x;
-  uint32_t* bloom = a.bloom + (size_t)blockIdx.x * kBloomWords;
+  carve<T>(s, smem_raw, MODE, a, warp);
+  uint32_t* bloom = a.bloom + ((size_t)blockIdx.x * warps + warp) * kBloomWords;
 
   for (;;) {
     uint32_t q = 0;
@@ -615,21 +747,23 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
     q = __shfl_sync(kFull, q, 0);
     if (q >= a.Q) break;
 
-    // ---- per-query setup: query -> smem, bloom filter cleared, PQ table built in place ----
+    Prof pf;
+    pf.start();
+    // ---- per-query setup: query -> smem, bloom filter cleared ----
     uint2 my_nb = fetch_adj(a, a.medoid);  // the first hop's adjacency row travels during the setup
     __syncwarp();
     load_query<T>(a, q, s.q_f);
     {
       uint4* b4 = reinterpret_cast<uint4*>(bloom);
-      for (uint32_t i = lane; i < kBloomWords / 4; i += kThreads) b4[i] = make_uint4(0, 0, 0, 0);
+      for (uint32_t i = lane; i < kBloomWords / 4; i += 32) b4[i] = make_uint4(0, 0, 0, 0);
     }
     if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
     __syncwarp();
-    if (MODE != kExact) {
-      build_pq_table(a, s.q_f, s.lut);
-      __syncwarp();
-    }
+    if (MODE != kExact)
+      for (uint32_t j = lane; j < a.D; j += 32) s.qc[j] = __fsub_rn(s.q_f[j], __ldg(a.centroid + j));
+    __syncwarp();
     __threadfence_block();  // the cleared filter is ordered before this query's tests and insertions
+    pf.tick(PT_SETUP);
 
     uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1, sum_deg = 0, n_pass = 0, deg = 0, pos0 = 0;
     auto log_parent = [&](uint32_t node) {
@@ -642,23 +776,24 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
-      uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, true, &deg);
+      uint32_t n = expand<T, MODE, CHUNK4>(a, s, bloom, my_nb, true, &deg, pf);
       sum_deg += deg; n_pass += n;
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
       uint32_t parent = b.id, mark = have ? b.id : 0x01010101u;
       if (have) log_parent(parent);
-      uint32_t pend_n = n, pend_nb = min(n, a.L), scan_from = 0;
+      uint32_t pend_n = n, pend_nb = min(n, a.L), pend_below = 0, scan_from = 0;
+      float pend_maxd = 0.0f;
       while (have || pend_n > 0) {
         if (have) my_nb = fetch_adj(a, parent);  // in flight during the merge
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
-          ws = merge_worklist(a, s, pend_n, pend_nb, ws, iter == 1, mark, &pos0);
+          ws = merge_worklist(a, s, pend_n, pend_nb, pend_below, pend_maxd, ws, iter == 1, mark, &pos0);
           scan_from = min(scan_from, pos0);
         }
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
         n = 0;
-        if (have) { n = expand<T, MODE>(a, s, bloom, my_nb, false, &deg); sum_deg += deg; n_pass += n; }
+        if (have) { n = expand<T, MODE, CHUNK4>(a, s, bloom, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
@@ -674,6 +809,8 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
         }
         if (have) log_parent(parent);
         pend_n = n;
+        pend_below = b.below;
+        pend_maxd = maxd;
         pend_nb = n ? admit_count(b.below, n, ws, a.L) : 0u;
         if (iter == a.max_iter - 1) break;
       }
@@ -685,10 +822,12 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-        const uint32_t n = expand<T, MODE>(a, s, bloom, my_nb, first, &deg);
+        const uint32_t n = expand<T, MODE, CHUNK4>(a, s, bloom, my_nb, first, &deg, pf);
         sum_deg += deg; n_pass += n;
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
         const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
+        pf.tick(PT_SCAN);
+        pf.count(PT_HOPS);
         uint32_t nb;
         bool have = false, from_new = false;
         if (first) {
@@ -706,26 +845,34 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
         log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
         const bool capped = iter == a.max_iter - 1;
         if (!capped) my_nb = fetch_adj(a, parent);  // in flight during the merge
+        pf.tick(PT_DECIDE);
         if (nb > 0) {
-          ws = merge_worklist(a, s, n, nb, ws, first, from_new ? parent : kNone, &pos0);
+          ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, first, from_new ? parent : kNone, &pos0);
           scan_from = min(scan_from, pos0);
+          pf.count(PT_MERGES);
         }
         __syncwarp();
+        pf.tick(PT_MERGE);
         fu = scan_unvisited(s, scan_from, ws);
+        pf.tick(PT_UNVIS);
         if (capped) break;
         ++iter;
       }
       if (MODE == kExact) {
         // top-k = head of the worklist (Exact parANN.cu:1273-1276)
         __syncwarp();
-        for (uint32_t r = lane; r < a.k; r += kThreads) {
+        for (uint32_t r = lane; r < a.k; r += 32) {
           a.out_ids[(size_t)q * a.k + r] = r < ws ? (uint64_t)s.w_id[r] : 0xFFFFFFFFull;
           a.out_dists[(size_t)q * a.k + r] = r < ws ? s.w_d[r] : 3.402823466e+38f;
         }
       } else {
         rerank_and_write<T>(a, s, q, ncand);
+        pf.tick(PT_RERANK);
       }
     }
+#ifdef BANG_PHASE_TIMERS
+    if (lane == 0 && a.st_phase) for (int i = 0; i < PT_COUNT; ++i) a.st_phase[(size_t)q * PT_COUNT + i] = pf.acc[i];
+#endif
     if (lane == 0) {
       if (a.dump_ids) {
         a.dump_ids[(size_t)q * a.dump_stride] = a.medoid;
@@ -741,13 +888,38 @@ __global__ void __launch_bounds__(kThreads) bang_search_kernel(const SearchArgs 
 
 // Standalone stage-1 kernel (parity test of populate_pqDist_par): one warp per query, table to global.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) pq_table_kernel(const SearchArgs a, float* tables) {
+__global__ void __launch_bounds__(32) pq_table_kernel(const SearchArgs a, float* tables) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* q_f = reinterpret_cast<float*>(smem_raw);
   const uint32_t q = blockIdx.x;
   load_query<T>(a, q, q_f);
   __syncwarp();
   build_pq_table(a, q_f, tables + (size_t)q * a.n_chunks * 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch geometry: how many query warps fit in one CTA / SM
+// ------------------------------------------------------------------------------------------------
+struct LaunchGeom { int warps_per_cta; int ctas_per_sm; size_t smem; };
+template <typename T>
+inline LaunchGeom launch_geometry(int mode, uint32_t D, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap,
+                                  size_t smem_optin_per_block, size_t smem_per_sm, int max_warps_per_sm) {
+  const size_t shared = cta_shared_bytes(mode, D, n_chunks), per = warp_private_bytes<T>(mode, D, vec_units, L, cand_cap);
+  LaunchGeom g{0, 0, 0};
+  if (shared + per > smem_optin_per_block) return g;
+  int w = (int)((smem_optin_per_block - shared) / per);
+  if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
+  if (max_warps_per_sm > 0 && w > max_warps_per_sm) w = max_warps_per_sm;
+  g.warps_per_cta = w;
+  g.smem = shared + (size_t)w * per;
+  // several small CTAs per SM when the shared part is small (e.g. exact mode): bounded by smem and 64 warps/SM
+  int c = (int)(smem_per_sm / (g.smem + 1024));
+  if (c < 1) c = 1;
+  if (c * w > 64) c = 64 / w;
+  if (max_warps_per_sm > 0 && c * w > max_warps_per_sm) c = max_warps_per_sm / w;
+  if (c < 1) c = 1;
+  g.ctas_per_sm = c;
+  return g;
 }
 
 }  // namespace bang
