@@ -46,7 +46,17 @@ constexpr int kMaxWarpsPerCta = 16;  // 512 threads: up to 128 registers per thr
 constexpr int kMaxR = 64;               // MAX_R, bang_search.cu:35
 constexpr int kListCap = kMaxR + 8;     // medoid + R neighbours, padded
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
-constexpr uint32_t kBloomWords = 12512u;  // ceil(399887/32)=12497, padded to a multiple of 32 words
+// The visited filter has the reference's semantics — a 399887-slot bit array addressed by two hashes — but is
+// stored sparsely: 1569 blocks of 255 slots, each block = 16 bytes holding up to 15 one-byte offsets of its set
+// slots (0xFF = empty) plus a count byte.  A search sets a few thousand slots (0.8 % of the array), so 25 KB
+// replace the 50 KB bitmap (and the reference's 400 KB byte array) with identical answers; the filters of all
+// resident queries then fit in L2 next to the PQ codes (ncu: profiles/r1_*).  A block that ever holds more
+// than 15 slots spills into a per-query overflow list.
+constexpr uint32_t kVisBlocks = (kBfEntries + 254u) / 255u;        // 1569
+constexpr uint32_t kVisOvfCap = 255u;                               // overflow list entries
+constexpr uint32_t kVisBlockBytes = ((kVisBlocks * 16u + 127u) / 128u) * 128u;   // 25216
+constexpr uint32_t kVisSlotBytes = kVisBlockBytes + 4u * (kVisOvfCap + 1u);       // + counter + list
+constexpr uint32_t kBloomWords = kVisSlotBytes / 4u;  // size of one filter in 32-bit words (host allocation unit)
 constexpr uint32_t kNoNbr = 0xFFFFFFFFu;  // padding id in the HBM adjacency rows
 constexpr int kAdjBytes = kMaxR * 4;    // 256 B adjacency block at the head of each HBM row
 constexpr int kMaxShards = 8;
@@ -78,7 +88,7 @@ struct SearchArgs {
   const void* queries;      // device T[Q][q_dim]
   uint64_t* out_ids;        // device [Q][k]
   float* out_dists;         // device [Q][k] (query-major)
-  uint32_t* bloom;          // device [gridDim.x][kBloomWords]
+  uint32_t* bloom;          // device: one sparse visited filter (kVisSlotBytes) per resident query warp
   uint32_t* counter;        // device work counter (zeroed before launch)
   uint32_t* st_hops;        // device [Q] or null
   uint32_t* st_sumdeg;
@@ -183,14 +193,47 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_evict_first()));
   return r;
 }
-// bloom word: coherent at L2 (skips L1), kept with evict-last priority
-__device__ __forceinline__ uint32_t bloom_ld(const uint32_t* p) {
-  uint32_t r;
-  asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_evict_last()));
+// ---- sparse visited filter (see kVisBlocks) -------------------------------------------------------
+struct VisAddr { uint32_t blk, off; };  // block index and offset (0..254) of a slot
+__device__ __forceinline__ VisAddr vis_addr(uint32_t pos) {
+  VisAddr v;
+  v.blk = __umulhi(pos, 0x80808081u) >> 7;  // pos / 255 (exact for pos < 2^31)
+  v.off = pos - v.blk * 255u;
+  return v;
+}
+__device__ __forceinline__ uint4 vis_ld_block(const uint8_t* vis, uint32_t blk) {
+  uint4 r;
+  const uint8_t* p = vis + (size_t)blk * 16;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(l2_policy_evict_last()));
   return r;
 }
-__device__ __forceinline__ void bloom_or(uint32_t* p, uint32_t bit) {
-  asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" :: "l"(p), "r"(bit), "l"(l2_policy_evict_last()) : "memory");
+// is the slot set, given its block?  Bytes 0..14 hold offsets of set slots or 0xFF; byte 15 counts insertions.
+__device__ __forceinline__ bool vis_test(const uint8_t* vis, uint4 blk, uint32_t pos, uint32_t off) {
+  const uint32_t pat = off * 0x01010101u;
+  bool found = (__vcmpeq4(blk.x, pat) | __vcmpeq4(blk.y, pat) | __vcmpeq4(blk.z, pat) | (__vcmpeq4(blk.w, pat) & 0x00FFFFFFu)) != 0;
+  if (!found && (blk.w >> 24) > 15u) {  // the block spilled: scan the overflow list (rare)
+    const uint32_t* ovf = reinterpret_cast<const uint32_t*>(vis + kVisBlockBytes);
+    const uint32_t m = min(__ldcg(ovf), kVisOvfCap);
+    for (uint32_t i = 0; i < m && !found; ++i) found = __ldcg(ovf + 1 + i) == pos;
+  }
+  return found;
+}
+// set a slot (not currently set), in two steps so that nothing waits for the atomic's round trip:
+// vis_reserve bumps the block's count with one L2 atomic and returns the old count word; vis_commit, called
+// after the distance computations of the hop, stores the offset byte into the reserved position.
+__device__ __forceinline__ unsigned long long vis_reserve(uint8_t* vis, uint32_t blk) {
+  return atomicAdd(reinterpret_cast<unsigned long long*>(vis + (size_t)blk * 16 + 8), 1ull << 56);
+}
+__device__ __forceinline__ void vis_commit(uint8_t* vis, uint32_t pos, VisAddr a, unsigned long long old) {
+  const uint32_t idx = (uint32_t)(old >> 56);
+  if (idx < 15u) {
+    vis[(size_t)a.blk * 16 + idx] = (uint8_t)a.off;
+  } else {
+    uint32_t* ovf = reinterpret_cast<uint32_t*>(vis + kVisBlockBytes);
+    const uint32_t j = atomicAdd(ovf, 1u);
+    if (j < kVisOvfCap) ovf[1 + j] = pos;
+  }
 }
 
 // Exact squared L2 between one HBM row vector and the query (fp32 copy in shared memory).
@@ -356,11 +399,15 @@ __device__ __forceinline__ float adc_entry(const QState& s, uint32_t D, uint32_t
 // partial ADC sum of one 32-chunk group for lane t: chunks base+t, base+t+8, base+t+16, base+t+24 (ascending)
 template <bool CHUNK4>
 __device__ __forceinline__ float adc_group(const QState& s, const SearchArgs& a, uint32_t word, uint32_t base, uint32_t t, float sum) {
+  float e[4];
 #pragma unroll
-  for (int b = 0; b < 4; ++b) {
+  for (int b = 0; b < 4; ++b) {  // four independent chains, then the ordered sum
     const uint32_t c = base + t + 8 * b;
-    if (c < a.n_chunks) sum = __fadd_rn(sum, adc_entry<CHUNK4>(s, a.D, c, (word >> (8 * b)) & 0xff));
+    e[b] = (c < a.n_chunks) ? adc_entry<CHUNK4>(s, a.D, c, (word >> (8 * b)) & 0xff) : 0.0f;
   }
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    if (base + t + 8 * b < a.n_chunks) sum = __fadd_rn(sum, e[b]);
   return sum;
 }
 
@@ -399,14 +446,12 @@ struct Prof {
 };
 #endif
 
-struct BloomPos { uint32_t w1, b1, w2, b2; };
+struct VisPos { uint32_t p1, p2; };
 template <int MODE>
-__device__ __forceinline__ BloomPos bloom_pos(uint32_t id) {
-  BloomPos p;
-  const uint32_t p1 = hash1(id);
-  p.w1 = p1 >> 5; p.b1 = 1u << (p1 & 31);
-  if (MODE == kExact) { p.w2 = p.w1; p.b2 = p.b1; }  // BANG_Exactdistance tests hash 1 only (parANN.cu:1040-1066)
-  else { const uint32_t p2 = hash2(id); p.w2 = p2 >> 5; p.b2 = 1u << (p2 & 31); }
+__device__ __forceinline__ VisPos vis_pos(uint32_t id) {
+  VisPos p;
+  p.p1 = hash1(id);
+  p.p2 = (MODE == kExact) ? p.p1 : hash2(id);  // BANG_Exactdistance tests hash 1 only (parANN.cu:1040-1066)
   return p;
 }
 
@@ -423,7 +468,7 @@ __device__ __forceinline__ BloomPos bloom_pos(uint32_t id) {
 // Returns the number of accepted candidates; n_id/n_d hold them unordered; *deg_out = degree of the node.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, bool CHUNK4>
-__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint32_t* bloom, uint2 nb2, bool first,
+__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* vis, uint2 nb2, bool first,
                                            uint32_t* deg_out, Prof& pf) {
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
   const uint32_t id0 = nb2.x, id1 = nb2.y;
@@ -432,33 +477,53 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   if (__any_sync(kFull, id0 == 0x12345678u && id1 == 0x9abcdef0u)) printf("");  // forces the adjacency load to complete here
   pf.tick(PT_ADJWAIT);
 #endif
-  const BloomPos p0 = bloom_pos<MODE>(id0), p1 = bloom_pos<MODE>(id1);
+  const VisPos p0 = vis_pos<MODE>(id0), p1 = vis_pos<MODE>(id1);
+  const VisAddr a01 = vis_addr(p0.p1), a02 = vis_addr(p0.p2), a11 = vis_addr(p1.p1), a12 = vis_addr(p1.p2);
 #ifdef BANG_PHASE_TIMERS
-  if (__any_sync(kFull, p0.w1 == 0xFFFFFFFFu)) printf("");
+  if (__any_sync(kFull, p0.p1 == 0xFFFFFFFFu)) printf("");
   pf.tick(PT_HASH);
 #endif
+  // ins bit k: slot k (1 = hash 1, 2 = hash 2) of the id is not set yet and has to be inserted
   bool acc0 = v0, acc1 = v1;
+  uint32_t ins0 = (MODE == kExact) ? 1u : 3u, ins1 = ins0;
   if (!first) {
-    uint32_t x01 = 0, x02 = 0, x11 = 0, x12 = 0;
-    if (v0) { x01 = bloom_ld(bloom + p0.w1); if (MODE != kExact) x02 = bloom_ld(bloom + p0.w2); }
-    if (v1) { x11 = bloom_ld(bloom + p1.w1); if (MODE != kExact) x12 = bloom_ld(bloom + p1.w2); }
-    if (MODE == kExact) { acc0 = v0 && !(x01 & p0.b1); acc1 = v1 && !(x11 & p1.b1); }
-    else { acc0 = v0 && !((x01 & p0.b1) && (x02 & p0.b2)); acc1 = v1 && !((x11 & p1.b1) && (x12 & p1.b2)); }
+    bool s01 = false, s02 = false, s11 = false, s12 = false;
+    uint4 b01, b02, b11, b12;
+    if (v0) { b01 = vis_ld_block(vis, a01.blk); if (MODE != kExact) b02 = vis_ld_block(vis, a02.blk); }
+    if (v1) { b11 = vis_ld_block(vis, a11.blk); if (MODE != kExact) b12 = vis_ld_block(vis, a12.blk); }
+    if (v0) { s01 = vis_test(vis, b01, p0.p1, a01.off); s02 = (MODE == kExact) ? s01 : vis_test(vis, b02, p0.p2, a02.off); }
+    if (v1) { s11 = vis_test(vis, b11, p1.p1, a11.off); s12 = (MODE == kExact) ? s11 : vis_test(vis, b12, p1.p2, a12.off); }
+    acc0 = v0 && !(s01 && s02);
+    acc1 = v1 && !(s11 && s12);
+    ins0 = (s01 ? 0u : 1u) | ((MODE != kExact && !s02) ? 2u : 0u);
+    ins1 = (s11 ? 0u : 1u) | ((MODE != kExact && !s12) ? 2u : 0u);
+  }
+  if (MODE != kExact) {  // one id whose two hashes coincide sets the slot once
+    if (p0.p1 == p0.p2) ins0 &= 1u;
+    if (p1.p1 == p1.p2) ins1 &= 1u;
   }
   __syncwarp();  // every test precedes every insertion
 #ifdef BANG_PHASE_TIMERS
   if (__any_sync(kFull, acc0 && id0 == 0x12345678u)) printf("");
   pf.tick(PT_BLOOM);
 #endif
-  if (acc0) { bloom_or(bloom + p0.w1, p0.b1); if (MODE != kExact) bloom_or(bloom + p0.w2, p0.b2); }  // fire and forget
-  if (acc1) { bloom_or(bloom + p1.w1, p1.b1); if (MODE != kExact) bloom_or(bloom + p1.w2, p1.b2); }
+  if (!acc0) ins0 = 0;
+  if (!acc1) ins1 = 0;
+  unsigned long long r01 = 0, r02 = 0, r11 = 0, r12 = 0, rm1 = 0, rm2 = 0;
+  if (ins0 & 1u) r01 = vis_reserve(vis, a01.blk);
+  if (ins0 & 2u) r02 = vis_reserve(vis, a02.blk);
+  if (ins1 & 1u) r11 = vis_reserve(vis, a11.blk);
+  if (ins1 & 2u) r12 = vis_reserve(vis, a12.blk);
   uint32_t pre = 0;
+  VisPos pm{0, 0};
+  VisAddr am1{0, 0}, am2{0, 0};
   if (first) {
     pre = 1;
     if (lane == 0) {
-      const BloomPos pm = bloom_pos<MODE>(a.medoid);
-      bloom_or(bloom + pm.w1, pm.b1);
-      if (MODE != kExact) bloom_or(bloom + pm.w2, pm.b2);
+      pm = vis_pos<MODE>(a.medoid);
+      am1 = vis_addr(pm.p1); am2 = vis_addr(pm.p2);
+      rm1 = vis_reserve(vis, am1.blk);
+      if (MODE != kExact && pm.p2 != pm.p1) rm2 = vis_reserve(vis, am2.blk);
       s.n_id[0] = a.medoid;
     }
   }
@@ -517,6 +582,15 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       sum = tree8(sum);
       if (t == 0 && k < n) s.n_d[k] = sum;
     }
+  }
+  // the reserved filter bytes: the atomics have long returned
+  if (ins0 & 1u) vis_commit(vis, p0.p1, a01, r01);
+  if (ins0 & 2u) vis_commit(vis, p0.p2, a02, r02);
+  if (ins1 & 1u) vis_commit(vis, p1.p1, a11, r11);
+  if (ins1 & 2u) vis_commit(vis, p1.p2, a12, r12);
+  if (first && lane == 0) {
+    vis_commit(vis, pm.p1, am1, rm1);
+    if (MODE != kExact && pm.p2 != pm.p1) vis_commit(vis, pm.p2, am2, rm2);
   }
   __syncwarp();
   pf.tick(PT_LUT);
@@ -739,7 +813,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
   }
   QState s;
   carve<T>(s, smem_raw, MODE, a, warp);
-  uint32_t* bloom = a.bloom + ((size_t)blockIdx.x * warps + warp) * kBloomWords;
+  uint8_t* vis = reinterpret_cast<uint8_t*>(a.bloom) + ((size_t)blockIdx.x * warps + warp) * kVisSlotBytes;
 
   for (;;) {
     uint32_t q = 0;
@@ -754,8 +828,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
     __syncwarp();
     load_query<T>(a, q, s.q_f);
     {
-      uint4* b4 = reinterpret_cast<uint4*>(bloom);
-      for (uint32_t i = lane; i < kBloomWords / 4; i += 32) b4[i] = make_uint4(0, 0, 0, 0);
+      uint4* b4 = reinterpret_cast<uint4*>(vis);
+      for (uint32_t i = lane; i < kVisBlocks; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
+      if (lane == 0) *reinterpret_cast<uint32_t*>(vis + kVisBlockBytes) = 0;  // overflow counter
     }
     if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
     __syncwarp();
@@ -776,7 +851,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
-      uint32_t n = expand<T, MODE, CHUNK4>(a, s, bloom, my_nb, true, &deg, pf);
+      uint32_t n = expand<T, MODE, CHUNK4>(a, s, vis, my_nb, true, &deg, pf);
       sum_deg += deg; n_pass += n;
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
@@ -793,7 +868,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
         n = 0;
-        if (have) { n = expand<T, MODE, CHUNK4>(a, s, bloom, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
+        if (have) { n = expand<T, MODE, CHUNK4>(a, s, vis, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
@@ -822,7 +897,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-        const uint32_t n = expand<T, MODE, CHUNK4>(a, s, bloom, my_nb, first, &deg, pf);
+        const uint32_t n = expand<T, MODE, CHUNK4>(a, s, vis, my_nb, first, &deg, pf);
         sum_deg += deg; n_pass += n;
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
         const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
