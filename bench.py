@@ -105,11 +105,12 @@ def make_index(wl: dict, workdir: str, device, builder: str, rank: int, world: i
     """Rank 0 generates the dataset + index files; the other ranks wait for them (same box)."""
     import bang_b200  # noqa: F401
     from bang_b200 import builder as B
-    prefix = os.path.join(workdir, f"{wl['dtype']}_{wl['n']}_{wl['d']}")
+    nq = wl["q"] * max(1, world)  # weak scaling: every rank searches its own batch of wl["q"] queries
+    prefix = os.path.join(workdir, f"{wl['dtype']}_{wl['n']}_{wl['d']}_q{nq}")
     done = prefix + ".done"
     if rank == 0 and not os.path.exists(done):
         t0 = time.time()
-        info = B.make_fixture_auto(prefix, wl["n"], wl["d"], wl["dtype"], wl["q"], wl["m"], k_gt=100, device=device,
+        info = B.make_fixture_auto(prefix, wl["n"], wl["d"], wl["dtype"], nq, wl["m"], k_gt=100, device=device,
                                    builder=builder)
         log(f"[bench] index built in {time.time() - t0:.1f}s ({info})")
         with open(done, "w") as f:
@@ -224,6 +225,32 @@ def cpu_baseline_sample(prefix, wl, queries, L, target_s=12.0):
                 sample=f"{n2} of {len(queries)} queries at L={L}, oracle/bang_oracle.c with OpenMP over queries")
 
 
+def reference_cuda_run(prefix, wl, paths, Q, L, gt_ids, gt_d):
+    """The UNMODIFIED reference (BANG_Base built from /root/reference into oracle/_ref, sm_100a) on this GPU over the
+    same index files: its own BANGSearch<T> API through oracle/ref_driver.cpp, 4 runs, first discarded (the
+    authors' protocol, BANG_Inmemory/parANN.h:30-31).  Comparison only; PQ modes only."""
+    from bang_b200 import recall
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(exe) or wl["mode"] == "exact":
+        return None
+    out = os.path.join(os.path.dirname(prefix), "ref_ids.bin")
+    dt = {"uint8": "uint8", "int8": "int8", "float": "float"}[wl["dtype"]]
+    try:
+        r = subprocess.run([exe, prefix, paths.query, str(Q), str(K), str(L), dt, out, "4"], capture_output=True, text=True,
+                           timeout=900)
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+    if r.returncode != 0:
+        return {"error": (r.stdout[-300:] + r.stderr[-300:])}
+    ms = [float(l.split()[2]) for l in r.stdout.splitlines() if l.startswith("RUN ")]
+    ids = np.fromfile(out, dtype=np.uint64).reshape(Q, K)
+    rec = recall.calculate_recall(gt_ids[:Q], gt_d[:Q], ids, K)
+    use = ms[1:] if len(ms) > 1 else ms
+    gm = float(np.exp(np.mean(np.log(use))))
+    return {"qps": Q / (gm * 1e-3), "ms": gm, "runs_ms": ms, "L": L, "recall_at_10": round(rec, 2),
+            "what": "unmodified BANG_Base (oracle/_ref/libbang.so, nvcc -arch sm_100a) via its BANGSearch<T> API, wall clock around bang_query"}
+
+
 def run_b200(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -248,12 +275,13 @@ def run_b200(args):
     os.makedirs(workdir, exist_ok=True)
     prefix = make_index(wl, workdir, device, args.builder, rank, world)
     paths = formats.IndexPaths(prefix)
-    queries = formats.read_bin(paths.query, api.NP[wl["dtype"]])[: wl["q"]]
+    queries = formats.read_bin(paths.query, api.NP[wl["dtype"]])[: wl["q"] * world]
     gt_ids, gt_d = formats.read_truthset(paths.truth)
 
-    # replicated index, query batch split contiguously across ranks, no collective on the data path
-    per = (len(queries) + world - 1) // world
-    lo, hi = rank * per, min(len(queries), (rank + 1) * per)
+    # replicated index; every rank searches its own batch of wl["q"] queries (weak scaling), no collective on
+    # the data path
+    per = wl["q"]
+    lo, hi = rank * per, (rank + 1) * per
     my_q = np.ascontiguousarray(queries[lo:hi])
 
     search = api.BANGSearch(wl["dtype"], wl["mode"], device=local)
@@ -267,7 +295,7 @@ def run_b200(args):
         found = {90.0: (args.L, float("nan")), 95.0: (args.L95 or args.L, float("nan"))}
         curve = []
     else:
-        found, curve = pick_L(search, queries, gt_ids, gt_d)  # every rank runs the (deterministic) sweep on all queries
+        found, curve = pick_L(search, queries[:per], gt_ids[:per], gt_d[:per])  # every rank: same deterministic sweep on batch 0
         if 90.0 not in found or 95.0 not in found:
             raise SystemExit(f"recall targets not reached in the L sweep: {curve}")
     if rank == 0:
@@ -332,16 +360,17 @@ def run_b200(args):
     tm = p90["timing"]
     Qtot = len(queries)
     esz = 4 if wl["dtype"] == "float" else 1
+    info = search.info()
     line = {
         "metric": "QPS at recall@10 >= 0.90 (batched greedy Vamana search)",
         "value": p90["qps"], "unit": "QPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": p90["ms"], "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "ms_per_step": p90["ms"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8 codes / fp32 ADC sums" if wl["mode"] != "exact" else "fp32",
         "data": "synthetic clustered (Gaussian mixture), index built on the box by the committed builder",
         "config": {"workload": f"{wl['label']}: N={wl['n']} D={wl['d']} {wl['dtype']} R=64 "
                                + (f"PQ m={wl['m']}" if wl["m"] else "no PQ") + f", Q={Qtot}, k={K}, mode={wl['mode']}",
                    "L_at_recall_90": p90["L"], "recall_at_10": round(p90["recall"], 2),
-                   "parallelism": f"index replicated, queries split x{world}, no collective",
+                   "parallelism": f"index replicated on {world} GPU(s), one batch of {wl['q']} queries per GPU, no collective",
                    "l2": "256 MiB buffer written between timed iterations; index (rows+codes) larger than L2",
                    "builder": args.builder},
         "e2e": {"value": p90["e2e_qps"], "unit": "QPS", "ms_per_step": p90["e2e_ms"],
@@ -358,6 +387,11 @@ def run_b200(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if world == 1 and not args.no_ref_cuda:
+        search.bang_unload()
+        ref = reference_cuda_run(prefix, wl, paths, wl["q"], p90["L"], gt_ids, gt_d)
+        if ref:
+            line["reference_cuda_b200"] = ref
     print(json.dumps(line), flush=True)
 
 
@@ -447,6 +481,7 @@ def main():
     ap.add_argument("--builder", default="auto", choices=["auto", "gpu", "cpu"])
     ap.add_argument("--workdir", default="")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
