@@ -310,21 +310,12 @@ def run_b200(args):
     clocks = sampler.stop()
 
     # gather results: ids for the recall check, timings for max-over-ranks
-    def allmax(xs):
-        if world == 1:
-            return list(xs)
-        import torch.distributed as dist
-        t = torch.tensor(xs, dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.tolist()
+    from bang_b200 import sharding
 
-    def gather_np(a):
-        if world == 1:
-            return a
-        import torch.distributed as dist
-        outs = [None] * world
-        dist.all_gather_object(outs, a)
-        return np.concatenate(outs, 0)
+    def allmax(xs):
+        return sharding.max_over_ranks(xs, device=device)
+
+    gather_np = sharding.gather_rows
 
     out = {}
     for tgt in (90.0, 95.0):

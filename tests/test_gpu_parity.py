@@ -229,3 +229,17 @@ def test_against_reference_cuda_build(fixtures, name, tmp_path):
     print(f"{name}: identical top-k sets {same:.4f}; recall ref {r_ref:.2f} new {r_new:.2f}")
     assert same >= 0.99
     assert abs(r_ref - r_new) <= 0.1 + 1e-9
+
+
+def test_sharded_graph_p2p_two_gpus():
+    """Graph rows sharded over 2 GPUs, peers read with P2P loads in the kernel: bit-exact vs the oracle."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on one box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "p2p_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ids == oracle: True") == 6

@@ -1,0 +1,69 @@
+"""World-size-2 checks of the multi-GPU host logic on CPU (gloo, 127.0.0.1): batch split, slowest-rank timing,
+result gather, and the shard-handle exchange protocol (with a stand-in for the CUDA IPC calls)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bang_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _FakeSearch:
+    def __init__(self, rank):
+        self.rank = rank
+        self.imported = {}
+
+    def export_shard(self):
+        return bytes([self.rank]) * 64
+
+    def import_shard(self, shard, handle):
+        assert len(handle) == 64
+        self.imported[shard] = handle
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q = 7
+        sl = sharding.rank_batch(q, rank)
+        mine = np.arange(world * q)[sl].reshape(-1, 1).astype(np.uint64)
+        allr = sharding.gather_rows(mine)
+        t = sharding.max_over_ranks([1.0 + rank, 5.0 - rank])
+        fs = _FakeSearch(rank)
+        sharding.exchange_shards(fs, rank, world)
+        out[rank] = (allr.ravel().tolist(), t, sorted(fs.imported), [fs.imported[k][0] for k in sorted(fs.imported)])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_gloo():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for rank in range(world):
+        allr, t, imp, first_bytes = out[rank]
+        assert allr == list(range(14))              # rank-ordered concatenation of the per-rank batches
+        assert t == [2.0, 5.0]                      # slowest rank
+        assert imp == [1 - rank] and first_bytes == [1 - rank]   # imported exactly the peer's shard
+
+
+def test_split_batch_is_balanced_and_covers():
+    for n, w in [(10000, 8), (10, 3), (7, 8), (1, 2)]:
+        sl = [sharding.split_batch(n, r, w) for r in range(w)]
+        sizes = [s.stop - s.start for s in sl]
+        assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+        assert sl[0].start == 0 and all(sl[i].stop == sl[i + 1].start for i in range(w - 1))
