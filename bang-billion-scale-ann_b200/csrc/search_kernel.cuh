@@ -193,6 +193,11 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_evict_first()));
   return r;
 }
+// Speculative L2 prefetch of one 32-byte sector: issued for the PQ codes of ALL neighbours of the expanded node
+// as soon as their ids arrive, i.e. in parallel with the visited-filter round trip.  The real code loads (only
+// for the candidates that pass the filter) then hit L2 instead of paying a second dependent DRAM access.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 // ---- sparse visited filter (see kVisBlocks) -------------------------------------------------------
 struct VisAddr { uint32_t blk, off; };  // block index and offset (0..254) of a slot
 __device__ __forceinline__ VisAddr vis_addr(uint32_t pos) {
@@ -477,6 +482,10 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   if (__any_sync(kFull, id0 == 0x12345678u && id1 == 0x9abcdef0u)) printf("");  // forces the adjacency load to complete here
   pf.tick(PT_ADJWAIT);
 #endif
+  if (MODE != kExact) {  // codes of every neighbour towards L2 while the filter is being consulted
+    if (v0) prefetch_l2(a.codes + (size_t)id0 * a.code_stride);
+    if (v1) prefetch_l2(a.codes + (size_t)id1 * a.code_stride);
+  }
   const VisPos p0 = vis_pos<MODE>(id0), p1 = vis_pos<MODE>(id1);
   const VisAddr a01 = vis_addr(p0.p1), a02 = vis_addr(p0.p2), a11 = vis_addr(p1.p1), a12 = vis_addr(p1.p2);
 #ifdef BANG_PHASE_TIMERS

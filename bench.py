@@ -479,6 +479,12 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == "__main__":
