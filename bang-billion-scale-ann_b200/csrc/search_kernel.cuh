@@ -182,15 +182,22 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
+// createpolicy is not free (a few instructions per use): the kernel creates both policies once and keeps them in
+// registers; helpers without an explicit policy argument are for the cold paths (builder, re-rank).
+__device__ __forceinline__ uint4 ld_nc_u4(const void* p, uint64_t pol) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(l2_policy_evict_first()));
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
   return r;
 }
-__device__ __forceinline__ uint32_t ld_nc_u32(const void* p) {
+__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_nc_u32(const void* p, uint64_t pol) {
   uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_evict_first()));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
   return r;
 }
 // Speculative L2 prefetch of one 32-byte sector: issued for the PQ codes of ALL neighbours of the expanded node
@@ -206,17 +213,20 @@ __device__ __forceinline__ VisAddr vis_addr(uint32_t pos) {
   v.off = pos - v.blk * 255u;
   return v;
 }
-__device__ __forceinline__ uint4 vis_ld_block(const uint8_t* vis, uint32_t blk) {
+__device__ __forceinline__ uint4 vis_ld_block(const uint8_t* vis, uint32_t blk, uint64_t pol_keep) {
   uint4 r;
   const uint8_t* p = vis + (size_t)blk * 16;
   asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(l2_policy_evict_last()));
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol_keep));
   return r;
 }
 // is the slot set, given its block?  Bytes 0..14 hold offsets of set slots or 0xFF; byte 15 counts insertions.
 __device__ __forceinline__ bool vis_test(const uint8_t* vis, uint4 blk, uint32_t pos, uint32_t off) {
   const uint32_t pat = off * 0x01010101u;
-  bool found = (__vcmpeq4(blk.x, pat) | __vcmpeq4(blk.y, pat) | __vcmpeq4(blk.z, pat) | (__vcmpeq4(blk.w, pat) & 0x00FFFFFFu)) != 0;
+  // "does any byte equal off": (x - 0x01..) & ~x & 0x80.. is non-zero iff x has a zero byte (exact for the any-test)
+  const uint32_t x0 = blk.x ^ pat, x1 = blk.y ^ pat, x2 = blk.z ^ pat, x3 = (blk.w ^ pat) | 0xFF000000u;  // byte 15 = count
+  bool found = ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3)) &
+                0x80808080u) != 0;
   if (!found && (blk.w >> 24) > 15u) {  // the block spilled: scan the overflow list (rare)
     const uint32_t* ovf = reinterpret_cast<const uint32_t*>(vis + kVisBlockBytes);
     const uint32_t m = min(__ldcg(ovf), kVisOvfCap);
@@ -311,6 +321,7 @@ struct QState {
   uint32_t* s_id;    // [kListCap] the admitted ones, sorted by (dist, id)
   float* s_d;
   uint32_t* cand_id; // [cand_cap] expanded-node log (PQ modes)
+  uint64_t pol_stream, pol_keep;  // L2 policies: evict-first (one-touch gathers), evict-last (visited filter)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -384,35 +395,40 @@ __device__ __forceinline__ void build_pq_table(const SearchArgs& a, const float*
 // reading the pivot row from the CTA-shared table — hence bit-identical to the reference's tbl[c][code].
 template <bool CHUNK4>
 __device__ __forceinline__ float adc_entry(const QState& s, uint32_t D, uint32_t c, uint32_t code) {
-  const float* p = s.piv_s + (size_t)code * D;
   float acc = 0.0f;
   if (CHUNK4) {
-    const float4 pv = *reinterpret_cast<const float4*>(p + 4 * c);
-    const float4 qv = *reinterpret_cast<const float4*>(s.qc + 4 * c);
+    // 32-bit shared-space addresses, one 16-byte load each for the pivot row slice and the query residual
+    const uint32_t pa = (uint32_t)__cvta_generic_to_shared(s.piv_s) + (code * D + 4u * c) * 4u;
+    const uint32_t qa = (uint32_t)__cvta_generic_to_shared(s.qc) + 16u * c;
+    float4 pv, qv;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w) : "r"(pa));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(qv.x), "=f"(qv.y), "=f"(qv.z), "=f"(qv.w) : "r"(qa));
     float d;
     d = __fsub_rn(pv.x, qv.x); acc = __fmaf_rn(d, d, acc);
     d = __fsub_rn(pv.y, qv.y); acc = __fmaf_rn(d, d, acc);
     d = __fsub_rn(pv.z, qv.z); acc = __fmaf_rn(d, d, acc);
     d = __fsub_rn(pv.w, qv.w); acc = __fmaf_rn(d, d, acc);
   } else {
+    const float* p = s.piv_s + (size_t)code * D;
     const uint32_t j0 = s.coff_s[c], j1 = s.coff_s[c + 1];
     for (uint32_t j = j0; j < j1; ++j) { const float d = __fsub_rn(p[j], s.qc[j]); acc = __fmaf_rn(d, d, acc); }
   }
   return acc;
 }
 
-// partial ADC sum of one 32-chunk group for lane t: chunks base+t, base+t+8, base+t+16, base+t+24 (ascending)
-template <bool CHUNK4>
+// partial ADC sum of one 32-chunk group for lane t: chunks base+t, base+t+8, base+t+16, base+t+24 (ascending).
+// FULL: the group is known to be complete (n_chunks is a multiple of 32), no bounds checks.
+template <bool CHUNK4, bool FULL>
 __device__ __forceinline__ float adc_group(const QState& s, const SearchArgs& a, uint32_t word, uint32_t base, uint32_t t, float sum) {
   float e[4];
 #pragma unroll
   for (int b = 0; b < 4; ++b) {  // four independent chains, then the ordered sum
     const uint32_t c = base + t + 8 * b;
-    e[b] = (c < a.n_chunks) ? adc_entry<CHUNK4>(s, a.D, c, (word >> (8 * b)) & 0xff) : 0.0f;
+    e[b] = (FULL || c < a.n_chunks) ? adc_entry<CHUNK4>(s, a.D, c, (word >> (8 * b)) & 0xff) : 0.0f;
   }
 #pragma unroll
   for (int b = 0; b < 4; ++b)
-    if (base + t + 8 * b < a.n_chunks) sum = __fadd_rn(sum, e[b]);
+    if (FULL || base + t + 8 * b < a.n_chunks) sum = __fadd_rn(sum, e[b]);
   return sum;
 }
 
@@ -424,11 +440,11 @@ __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, floa
 }
 
 // adjacency prefetch: lane l requests neighbour slots 2l and 2l+1 of `node`'s HBM row (one 256-byte request)
-__device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node) {
+__device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream) {
   uint2 r;
   const uint8_t* p = row_ptr(a, node) + 8 * (threadIdx.x & 31);
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
-               : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(l2_policy_evict_first()));
+               : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_stream));
   return r;
 }
 
@@ -498,8 +514,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   if (!first) {
     bool s01 = false, s02 = false, s11 = false, s12 = false;
     uint4 b01, b02, b11, b12;
-    if (v0) { b01 = vis_ld_block(vis, a01.blk); if (MODE != kExact) b02 = vis_ld_block(vis, a02.blk); }
-    if (v1) { b11 = vis_ld_block(vis, a11.blk); if (MODE != kExact) b12 = vis_ld_block(vis, a12.blk); }
+    if (v0) { b01 = vis_ld_block(vis, a01.blk, s.pol_keep); if (MODE != kExact) b02 = vis_ld_block(vis, a02.blk, s.pol_keep); }
+    if (v1) { b11 = vis_ld_block(vis, a11.blk, s.pol_keep); if (MODE != kExact) b12 = vis_ld_block(vis, a12.blk, s.pol_keep); }
     if (v0) { s01 = vis_test(vis, b01, p0.p1, a01.off); s02 = (MODE == kExact) ? s01 : vis_test(vis, b02, p0.p2, a02.off); }
     if (v1) { s11 = vis_test(vis, b11, p1.p1, a11.off); s12 = (MODE == kExact) ? s11 : vis_test(vis, b12, p1.p2, a12.off); }
     acc0 = v0 && !(s01 && s02);
@@ -555,13 +571,14 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       if (t == 0 && kb < n) s.n_d[kb] = db;
     }
   } else if (a.n_chunks <= 32) {
+    const bool full32 = a.n_chunks == 32;
     for (uint32_t k0 = 0; k0 < n; k0 += 16) {  // 16 candidates' code words in flight
       uint32_t w[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const uint32_t k = k0 + p * 4 + g;
         w[p] = 0;
-        if (k < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[k] * a.code_stride + 4 * t);
+        if (k < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[k] * a.code_stride + 4 * t, s.pol_stream);
       }
 #ifdef BANG_PHASE_TIMERS
       if (__any_sync(kFull, (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x12345678u)) printf("");
@@ -571,7 +588,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       for (int p = 0; p < 4; ++p) {
         if (k0 + p * 4 < n) {  // warp-uniform
           const uint32_t k = k0 + p * 4 + g;
-          const float sum = tree8(adc_group<CHUNK4>(s, a, w[p], 0, t, 0.0f));
+          const float part = full32 ? adc_group<CHUNK4, true>(s, a, w[p], 0, t, 0.0f) : adc_group<CHUNK4, false>(s, a, w[p], 0, t, 0.0f);
+          const float sum = tree8(part);
           if (t == 0 && k < n) s.n_d[k] = sum;
         }
       }
@@ -583,10 +601,10 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       const uint8_t* row = a.codes + (size_t)(k < n ? s.n_id[k] : 0u) * a.code_stride + 4 * t;
       float sum = 0.0f;
       for (uint32_t gg = 0; gg < groups; gg += 2) {
-        const uint32_t wa = ld_nc_u32(row + gg * 32);
-        const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32) : 0u;
-        sum = adc_group<CHUNK4>(s, a, wa, gg * 32, t, sum);
-        sum = adc_group<CHUNK4>(s, a, wb, (gg + 1) * 32, t, sum);
+        const uint32_t wa = ld_nc_u32(row + gg * 32, s.pol_stream);
+        const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32, s.pol_stream) : 0u;
+        sum = adc_group<CHUNK4, false>(s, a, wa, gg * 32, t, sum);
+        sum = adc_group<CHUNK4, false>(s, a, wb, (gg + 1) * 32, t, sum);
       }
       sum = tree8(sum);
       if (t == 0 && k < n) s.n_d[k] = sum;
@@ -822,6 +840,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
   }
   QState s;
   carve<T>(s, smem_raw, MODE, a, warp);
+  const uint64_t pol_stream = l2_policy_evict_first();
+  s.pol_stream = pol_stream;
+  s.pol_keep = l2_policy_evict_last();
   uint8_t* vis = reinterpret_cast<uint8_t*>(a.bloom) + ((size_t)blockIdx.x * warps + warp) * kVisSlotBytes;
 
   for (;;) {
@@ -833,7 +854,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
     Prof pf;
     pf.start();
     // ---- per-query setup: query -> smem, bloom filter cleared ----
-    uint2 my_nb = fetch_adj(a, a.medoid);  // the first hop's adjacency row travels during the setup
+    uint2 my_nb = fetch_adj(a, a.medoid, pol_stream);  // the first hop's adjacency row travels during the setup
     __syncwarp();
     load_query<T>(a, q, s.q_f);
     {
@@ -850,10 +871,11 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
     pf.tick(PT_SETUP);
 
     uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1, sum_deg = 0, n_pass = 0, deg = 0, pos0 = 0;
+    uint32_t* const dump_row = a.dump_ids ? a.dump_ids + (size_t)q * a.dump_stride : nullptr;
     auto log_parent = [&](uint32_t node) {
       if (lane == 0) {
         if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
-        if (a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = node;
+        if (dump_row && ncand < a.dump_stride) dump_row[ncand] = node;
       }
       if (ncand < a.cand_cap) ++ncand;
     };
@@ -869,7 +891,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
       uint32_t pend_n = n, pend_nb = min(n, a.L), pend_below = 0, scan_from = 0;
       float pend_maxd = 0.0f;
       while (have || pend_n > 0) {
-        if (have) my_nb = fetch_adj(a, parent);  // in flight during the merge
+        if (have) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
           ws = merge_worklist(a, s, pend_n, pend_nb, pend_below, pend_maxd, ws, iter == 1, mark, &pos0);
           scan_from = min(scan_from, pos0);
@@ -928,7 +950,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
         if (!from_new) { if (lane == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
         log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
         const bool capped = iter == a.max_iter - 1;
-        if (!capped) my_nb = fetch_adj(a, parent);  // in flight during the merge
+        if (!capped) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
         pf.tick(PT_DECIDE);
         if (nb > 0) {
           ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, first, from_new ? parent : kNone, &pos0);
