@@ -460,7 +460,8 @@ extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
   CUDA_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
   // Resident queries per SM: bounded by shared memory, and by default by the L2 share of their bloom
   // filters (50 KB each, kept in L2: 16 x 148 x 50 KB = 118 MB).  BANG_B200_WARPS_PER_SM overrides.
-  int max_warps = 16;
+  // The Exactdistance mode streams whole vectors and wants bytes in flight: 32 warps per SM (2 CTAs).
+  int max_warps = c->mode == BANG_MODE_EXACTDISTANCE ? 32 : 16;
   if (const char* e = getenv("BANG_B200_WARPS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) max_warps = v; }
   const LaunchGeom g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps);
   if (g.warps_per_cta < 1)

@@ -42,7 +42,7 @@
 namespace bang {
 
 constexpr int kThreads = 32;            // threads per query = one warp (see the header comment)
-constexpr int kMaxWarpsPerCta = 16;  // 512 threads: up to 128 registers per thread
+constexpr int kMaxWarpsPerCta = 16;  // 512 threads, 103 registers in the PQ kernels (17-24 warps make ptxas cap at 96 registers and spill: slower, profiles/r1_concurrency.md)
 constexpr int kMaxR = 64;               // MAX_R, bang_search.cu:35
 constexpr int kListCap = kMaxR + 8;     // medoid + R neighbours, padded
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
@@ -206,28 +206,27 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void* p, uint64_t pol) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ---- sparse visited filter (see kVisBlocks) -------------------------------------------------------
-struct VisAddr { uint32_t blk, off; };  // block index and offset (0..254) of a slot
+typedef uint32_t VisAddr;  // (block index << 8) | offset within the block (0..254)
 __device__ __forceinline__ VisAddr vis_addr(uint32_t pos) {
-  VisAddr v;
-  v.blk = __umulhi(pos, 0x80808081u) >> 7;  // pos / 255 (exact for pos < 2^31)
-  v.off = pos - v.blk * 255u;
-  return v;
+  const uint32_t blk = __umulhi(pos, 0x80808081u) >> 7;  // pos / 255 (exact for pos < 2^31)
+  return (blk << 8) | (pos - blk * 255u);
 }
-__device__ __forceinline__ uint4 vis_ld_block(const uint8_t* vis, uint32_t blk, uint64_t pol_keep) {
+__device__ __forceinline__ uint4 vis_ld_block(const uint8_t* vis, VisAddr a, uint64_t pol_keep) {
   uint4 r;
-  const uint8_t* p = vis + (size_t)blk * 16;
+  const uint8_t* p = vis + (size_t)(a >> 8) * 16;
   asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol_keep));
   return r;
 }
 // is the slot set, given its block?  Bytes 0..14 hold offsets of set slots or 0xFF; byte 15 counts insertions.
-__device__ __forceinline__ bool vis_test(const uint8_t* vis, uint4 blk, uint32_t pos, uint32_t off) {
-  const uint32_t pat = off * 0x01010101u;
+__device__ __forceinline__ bool vis_test(const uint8_t* vis, uint4 blk, VisAddr a) {
+  const uint32_t pat = (a & 255u) * 0x01010101u;
   // "does any byte equal off": (x - 0x01..) & ~x & 0x80.. is non-zero iff x has a zero byte (exact for the any-test)
   const uint32_t x0 = blk.x ^ pat, x1 = blk.y ^ pat, x2 = blk.z ^ pat, x3 = (blk.w ^ pat) | 0xFF000000u;  // byte 15 = count
   bool found = ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3)) &
                 0x80808080u) != 0;
   if (!found && (blk.w >> 24) > 15u) {  // the block spilled: scan the overflow list (rare)
+    const uint32_t pos = (a >> 8) * 255u + (a & 255u);
     const uint32_t* ovf = reinterpret_cast<const uint32_t*>(vis + kVisBlockBytes);
     const uint32_t m = min(__ldcg(ovf), kVisOvfCap);
     for (uint32_t i = 0; i < m && !found; ++i) found = __ldcg(ovf + 1 + i) == pos;
@@ -235,19 +234,19 @@ __device__ __forceinline__ bool vis_test(const uint8_t* vis, uint4 blk, uint32_t
   return found;
 }
 // set a slot (not currently set), in two steps so that nothing waits for the atomic's round trip:
-// vis_reserve bumps the block's count with one L2 atomic and returns the old count word; vis_commit, called
+// vis_reserve bumps the block's count byte with one L2 atomic and returns the old count word; vis_commit, called
 // after the distance computations of the hop, stores the offset byte into the reserved position.
-__device__ __forceinline__ unsigned long long vis_reserve(uint8_t* vis, uint32_t blk) {
-  return atomicAdd(reinterpret_cast<unsigned long long*>(vis + (size_t)blk * 16 + 8), 1ull << 56);
+__device__ __forceinline__ uint32_t vis_reserve(uint8_t* vis, VisAddr a) {
+  return atomicAdd(reinterpret_cast<uint32_t*>(vis + (size_t)(a >> 8) * 16 + 12), 1u << 24);
 }
-__device__ __forceinline__ void vis_commit(uint8_t* vis, uint32_t pos, VisAddr a, unsigned long long old) {
-  const uint32_t idx = (uint32_t)(old >> 56);
+__device__ __forceinline__ void vis_commit(uint8_t* vis, VisAddr a, uint32_t old) {
+  const uint32_t idx = old >> 24;
   if (idx < 15u) {
-    vis[(size_t)a.blk * 16 + idx] = (uint8_t)a.off;
+    vis[(size_t)(a >> 8) * 16 + idx] = (uint8_t)(a & 255u);
   } else {
     uint32_t* ovf = reinterpret_cast<uint32_t*>(vis + kVisBlockBytes);
     const uint32_t j = atomicAdd(ovf, 1u);
-    if (j < kVisOvfCap) ovf[1 + j] = pos;
+    if (j < kVisOvfCap) ovf[1 + j] = (a >> 8) * 255u + (a & 255u);
   }
 }
 
@@ -281,13 +280,32 @@ __device__ __forceinline__ float l2_row_8lane(const uint8_t* vec, const float* q
   return tree8(acc);
 }
 
-// Two rows at once (same arithmetic per row as l2_row_8lane, loads interleaved for memory-level parallelism).
+// Two rows at once (same arithmetic per row as l2_row_8lane: lane t accumulates its units in ascending order).
+// Loads are issued four units ahead per row, i.e. eight 16-byte requests in flight per lane (4 KB per warp), which
+// is what the long rows of the Exactdistance mode (3840 B at D = 960) need to keep HBM busy.
 template <typename T>
 __device__ __forceinline__ void l2_two_rows_8lane(const uint8_t* va, const uint8_t* vb, const float* q_f, uint32_t units,
                                                   uint32_t t, float* da, float* db) {
   constexpr int E = Elem<T>::kPerUnit;
   float acc_a = 0.0f, acc_b = 0.0f;
-  for (uint32_t u = t; u < units; u += 8) {
+  uint32_t u = t;
+  for (; u + 24 < units; u += 32) {
+    uint4 ra[4], rb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ra[i] = ld_nc_u4(va + (size_t)(u + 8 * i) * 16); rb[i] = ld_nc_u4(vb + (size_t)(u + 8 * i) * 16); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float f[E];
+      const float* qq = q_f + (u + 8 * i) * E;
+      Elem<T>::unpack(ra[i], f);
+#pragma unroll
+      for (int e = 0; e < E; ++e) { const float d = __fsub_rn(f[e], qq[e]); acc_a = __fmaf_rn(d, d, acc_a); }
+      Elem<T>::unpack(rb[i], f);
+#pragma unroll
+      for (int e = 0; e < E; ++e) { const float d = __fsub_rn(f[e], qq[e]); acc_b = __fmaf_rn(d, d, acc_b); }
+    }
+  }
+  for (; u < units; u += 8) {
     const uint4 ra = ld_nc_u4(va + (size_t)u * 16);
     const uint4 rb = ld_nc_u4(vb + (size_t)u * 16);
     float f[E];
@@ -505,7 +523,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   const VisPos p0 = vis_pos<MODE>(id0), p1 = vis_pos<MODE>(id1);
   const VisAddr a01 = vis_addr(p0.p1), a02 = vis_addr(p0.p2), a11 = vis_addr(p1.p1), a12 = vis_addr(p1.p2);
 #ifdef BANG_PHASE_TIMERS
-  if (__any_sync(kFull, p0.p1 == 0xFFFFFFFFu)) printf("");
+  if (__any_sync(kFull, a01 == 0xFFFFFFFFu)) printf("");
   pf.tick(PT_HASH);
 #endif
   // ins bit k: slot k (1 = hash 1, 2 = hash 2) of the id is not set yet and has to be inserted
@@ -514,18 +532,18 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   if (!first) {
     bool s01 = false, s02 = false, s11 = false, s12 = false;
     uint4 b01, b02, b11, b12;
-    if (v0) { b01 = vis_ld_block(vis, a01.blk, s.pol_keep); if (MODE != kExact) b02 = vis_ld_block(vis, a02.blk, s.pol_keep); }
-    if (v1) { b11 = vis_ld_block(vis, a11.blk, s.pol_keep); if (MODE != kExact) b12 = vis_ld_block(vis, a12.blk, s.pol_keep); }
-    if (v0) { s01 = vis_test(vis, b01, p0.p1, a01.off); s02 = (MODE == kExact) ? s01 : vis_test(vis, b02, p0.p2, a02.off); }
-    if (v1) { s11 = vis_test(vis, b11, p1.p1, a11.off); s12 = (MODE == kExact) ? s11 : vis_test(vis, b12, p1.p2, a12.off); }
+    if (v0) { b01 = vis_ld_block(vis, a01, s.pol_keep); if (MODE != kExact) b02 = vis_ld_block(vis, a02, s.pol_keep); }
+    if (v1) { b11 = vis_ld_block(vis, a11, s.pol_keep); if (MODE != kExact) b12 = vis_ld_block(vis, a12, s.pol_keep); }
+    if (v0) { s01 = vis_test(vis, b01, a01); s02 = (MODE == kExact) ? s01 : vis_test(vis, b02, a02); }
+    if (v1) { s11 = vis_test(vis, b11, a11); s12 = (MODE == kExact) ? s11 : vis_test(vis, b12, a12); }
     acc0 = v0 && !(s01 && s02);
     acc1 = v1 && !(s11 && s12);
     ins0 = (s01 ? 0u : 1u) | ((MODE != kExact && !s02) ? 2u : 0u);
     ins1 = (s11 ? 0u : 1u) | ((MODE != kExact && !s12) ? 2u : 0u);
   }
   if (MODE != kExact) {  // one id whose two hashes coincide sets the slot once
-    if (p0.p1 == p0.p2) ins0 &= 1u;
-    if (p1.p1 == p1.p2) ins1 &= 1u;
+    if (a01 == a02) ins0 &= 1u;
+    if (a11 == a12) ins1 &= 1u;
   }
   __syncwarp();  // every test precedes every insertion
 #ifdef BANG_PHASE_TIMERS
@@ -534,21 +552,20 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
 #endif
   if (!acc0) ins0 = 0;
   if (!acc1) ins1 = 0;
-  unsigned long long r01 = 0, r02 = 0, r11 = 0, r12 = 0, rm1 = 0, rm2 = 0;
-  if (ins0 & 1u) r01 = vis_reserve(vis, a01.blk);
-  if (ins0 & 2u) r02 = vis_reserve(vis, a02.blk);
-  if (ins1 & 1u) r11 = vis_reserve(vis, a11.blk);
-  if (ins1 & 2u) r12 = vis_reserve(vis, a12.blk);
+  uint32_t r01 = 0, r02 = 0, r11 = 0, r12 = 0, rm1 = 0, rm2 = 0;
+  if (ins0 & 1u) r01 = vis_reserve(vis, a01);
+  if (ins0 & 2u) r02 = vis_reserve(vis, a02);
+  if (ins1 & 1u) r11 = vis_reserve(vis, a11);
+  if (ins1 & 2u) r12 = vis_reserve(vis, a12);
   uint32_t pre = 0;
-  VisPos pm{0, 0};
-  VisAddr am1{0, 0}, am2{0, 0};
+  VisAddr am1 = 0, am2 = 0;
   if (first) {
     pre = 1;
     if (lane == 0) {
-      pm = vis_pos<MODE>(a.medoid);
+      const VisPos pm = vis_pos<MODE>(a.medoid);
       am1 = vis_addr(pm.p1); am2 = vis_addr(pm.p2);
-      rm1 = vis_reserve(vis, am1.blk);
-      if (MODE != kExact && pm.p2 != pm.p1) rm2 = vis_reserve(vis, am2.blk);
+      rm1 = vis_reserve(vis, am1);
+      if (MODE != kExact && am2 != am1) rm2 = vis_reserve(vis, am2);
       s.n_id[0] = a.medoid;
     }
   }
@@ -611,13 +628,13 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
     }
   }
   // the reserved filter bytes: the atomics have long returned
-  if (ins0 & 1u) vis_commit(vis, p0.p1, a01, r01);
-  if (ins0 & 2u) vis_commit(vis, p0.p2, a02, r02);
-  if (ins1 & 1u) vis_commit(vis, p1.p1, a11, r11);
-  if (ins1 & 2u) vis_commit(vis, p1.p2, a12, r12);
+  if (ins0 & 1u) vis_commit(vis, a01, r01);
+  if (ins0 & 2u) vis_commit(vis, a02, r02);
+  if (ins1 & 1u) vis_commit(vis, a11, r11);
+  if (ins1 & 2u) vis_commit(vis, a12, r12);
   if (first && lane == 0) {
-    vis_commit(vis, pm.p1, am1, rm1);
-    if (MODE != kExact && pm.p2 != pm.p1) vis_commit(vis, pm.p2, am2, rm2);
+    vis_commit(vis, am1, rm1);
+    if (MODE != kExact && am2 != am1) vis_commit(vis, am2, rm2);
   }
   __syncwarp();
   pf.tick(PT_LUT);
