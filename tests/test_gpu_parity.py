@@ -243,3 +243,22 @@ def test_sharded_graph_p2p_two_gpus():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ids == oracle: True") == 6
+
+
+DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "bang_search_dropin")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref not built (reference not mounted at build time)")
+def test_reference_driver_runs_on_this_library(fx_u8):
+    """The reference's own test_driver.cpp, compiled unchanged against include/bang.h and linked with libbang_b200.so,
+    sweeps L and prints its table; its recall column must equal ours."""
+    fx = fx_u8
+    out = subprocess.run([DROPIN, fx.prefix, fx.paths.query, fx.paths.truth, str(len(fx.queries)), "10", "uint8", "l2", "auto"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, BANG_B200_MODE="base"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = [l.split("\t") for l in out.stdout.splitlines() if l[:1].isdigit() and l.count("\t") >= 3]
+    got = {int(r[0]): float(r[3]) for r in rows}
+    assert 10 in got and 22 in got and max(got) > 400        # L = 10, 22, 34, ... (step 12, test_driver.cpp:409-417)
+    for L in (10, 34, 106):
+        ids, _, _, _ = _search(fx, "base", 10, L)
+        assert abs(got[L] - recall.calculate_recall(fx.gt_ids, fx.gt_dists, ids, 10)) < 0.01
