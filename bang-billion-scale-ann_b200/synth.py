@@ -149,13 +149,17 @@ def encode_pq(base: torch.Tensor, pivots: np.ndarray, centroid: np.ndarray, offs
 
 
 @torch.no_grad()
-def brute_force_gt(base: torch.Tensor, queries: torch.Tensor, k: int, block: int = 1 << 18):
+def brute_force_gt(base: torch.Tensor, queries: torch.Tensor, k: int, block: int = 1 << 18, q_block: int = 8192):
     """Exact kNN by squared L2.  Returns (ids u32 [nq][k], dists f32 [nq][k]) as numpy, ties ordered by id.
 
     Candidates are found with the matmul expansion in fp32 over blocks (over-fetching 2k per block),
     then the final k are re-scored with direct (a-b)^2 sums so distances are the exact ones the
-    search kernels produce (integers for u8/i8 inputs).
+    search kernels produce (integers for u8/i8 inputs).  Queries are processed q_block at a time so the
+    distance tile stays at q_block x block floats (8 GB).
     """
+    if queries.shape[0] > q_block:
+        parts = [brute_force_gt(base, queries[s:s + q_block], k, block, q_block) for s in range(0, queries.shape[0], q_block)]
+        return np.concatenate([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts], 0)
     dev = base.device
     nq = queries.shape[0]
     q = queries.float()
@@ -168,15 +172,18 @@ def brute_force_gt(base: torch.Tensor, queries: torch.Tensor, k: int, block: int
         d2 = qn[:, None] + (b * b).sum(1)[None, :] - 2.0 * (q @ b.T)
         kb = min(kk, b.shape[0])
         dd, ii = torch.topk(d2, kb, dim=1, largest=False)
+        del d2
         cat_d = torch.cat([best_d, dd], 1)
         cat_i = torch.cat([best_i, ii + s], 1)
         sel = torch.topk(cat_d, kk, dim=1, largest=False)[1]
         best_d = torch.gather(cat_d, 1, sel)
         best_i = torch.gather(cat_i, 1, sel)
-    # exact re-score
-    cand = base[best_i.reshape(-1)].float().reshape(nq, kk, -1)
-    diff = cand - q[:, None, :]
-    exact = (diff * diff).sum(2)
+    # exact re-score (in slices: nq x kk x d floats can be large for d = 960)
+    exact = torch.empty(nq, kk, device=dev)
+    for s in range(0, nq, 512):
+        cand = base[best_i[s:s + 512].reshape(-1)].float().reshape(-1, kk, base.shape[1])
+        diff = cand - q[s:s + 512, None, :]
+        exact[s:s + 512] = (diff * diff).sum(2)
     # order by (dist, id)
     order = torch.argsort(best_i, dim=1, stable=True)
     exact = torch.gather(exact, 1, order)
