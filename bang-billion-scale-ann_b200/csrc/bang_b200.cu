@@ -127,19 +127,27 @@ static size_t elem_size(int dtype) { return dtype == BANG_DT_FLOAT ? 4 : 1; }
 typedef void (*search_fn_t)(const SearchArgs);
 typedef void (*table_fn_t)(const SearchArgs, float*);
 
-template <typename T, bool C4>
+template <typename T, int CS>
 static search_fn_t pick_mode(int mode) {
   switch (mode) {
-    case BANG_MODE_BASE: return bang_search_kernel<T, kBase, C4>;
-    case BANG_MODE_INMEMORY: return bang_search_kernel<T, kInmemory, C4>;
-    default: return bang_search_kernel<T, kExact, false>;
+    case BANG_MODE_BASE: return bang_search_kernel<T, kBase, CS>;
+    case BANG_MODE_INMEMORY: return bang_search_kernel<T, kInmemory, CS>;
+    default: return bang_search_kernel<T, kExact, 0>;
   }
 }
-static search_fn_t pick_kernel(int dtype, int mode, bool chunk4) {
+template <typename T>
+static search_fn_t pick_cs(int mode, uint32_t cs) {
+  switch (cs) {
+    case 4: return pick_mode<T, 4>(mode);
+    case 3: return pick_mode<T, 3>(mode);
+    default: return pick_mode<T, 0>(mode);
+  }
+}
+static search_fn_t pick_kernel(int dtype, int mode, uint32_t cs) {
   switch (dtype) {
-    case BANG_DT_FLOAT: return chunk4 ? pick_mode<float, true>(mode) : pick_mode<float, false>(mode);
-    case BANG_DT_INT8: return chunk4 ? pick_mode<int8_t, true>(mode) : pick_mode<int8_t, false>(mode);
-    default: return chunk4 ? pick_mode<uint8_t, true>(mode) : pick_mode<uint8_t, false>(mode);
+    case BANG_DT_FLOAT: return pick_cs<float>(mode, cs);
+    case BANG_DT_INT8: return pick_cs<int8_t>(mode, cs);
+    default: return pick_cs<uint8_t>(mode, cs);
   }
 }
 static table_fn_t pick_table_kernel(int dtype) {
@@ -212,9 +220,11 @@ static int upload_pq(bang_b200_ctx* c, const PQHost& pq) {
   if (pq.chunk_off.back() != D) return set_err(BANG_E_FORMAT, "chunk offsets do not end at D");
   for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
     if (pq.chunk_off[i] > pq.chunk_off[i + 1]) return set_err(BANG_E_FORMAT, "chunk offsets not monotone");
-  c->chunk4 = (D % 4 == 0) ? 1u : 0u;
+  // uniform chunk size (4: SIFT 128/32, GIST...; 3: DEEP 96/32) selects a compile-time ADC path
+  c->chunk4 = pq.chunk_off.size() > 1 ? pq.chunk_off[1] - pq.chunk_off[0] : 0;
   for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
-    if (pq.chunk_off[i] != 4 * i || pq.chunk_off[i + 1] != 4 * (i + 1)) c->chunk4 = 0;
+    if (pq.chunk_off[i + 1] - pq.chunk_off[i] != c->chunk4) c->chunk4 = 0;
+  if (c->chunk4 != 4 && c->chunk4 != 3) c->chunk4 = 0;
   CUDA_TRY(cudaMalloc(&c->d_piv, pq.pivots.size() * 4));
   CUDA_TRY(cudaMemcpy(c->d_piv, pq.pivots.data(), pq.pivots.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&c->d_pivT, pivT.size() * 4));
@@ -454,7 +464,7 @@ extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
     if (!c->rows[s]) return set_err(BANG_E_STATE, "graph shard " + std::to_string(s) + " has not been imported");
   CUDA_TRY(cudaSetDevice(c->device));
   const uint32_t max_iter = max_iter_for(c->mode, c->L);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4 != 0);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4);
   int max_optin = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   CUDA_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
@@ -593,7 +603,7 @@ static int launch_search(bang_b200_ctx* c, const void* d_queries, int Q, uint64_
   apply_l2_window(c, st);
   CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4, st));
   const int grid = std::min((Q + c->warps_per_cta - 1) / c->warps_per_cta, c->grid);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4 != 0);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4);
   fn<<<grid, c->warps_per_cta * 32, c->smem, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->lastQ = Q;

@@ -286,7 +286,7 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
   if (max_batch == 0) max_batch = (uint32_t)std::max<uint64_t>(1024, std::min<uint64_t>(N / 50, 65536));
   const uint32_t MB = max_batch;
   // search scratch
-  auto kern = bang_search_kernel<T, kExact, false>;
+  auto kern = bang_search_kernel<T, kExact, 0>;
   int max_optin = 0, per_sm = 0;
   B_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   B_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));

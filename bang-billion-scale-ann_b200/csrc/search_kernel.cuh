@@ -74,7 +74,7 @@ struct SearchArgs {
   uint32_t n_chunks;
   const float* pivT;        // [D][256]   pivots transposed as the reference does at load (:281-285); stage-1 kernel only
   const float* piv;         // [256][D]   pivots in file order: the shared-memory table of the search kernel
-  uint32_t chunk4;          // 1 when every chunk spans exactly 4 dimensions (fast 16-byte path)
+  uint32_t chunk4;          // uniform chunk size when every chunk spans the same number of dimensions (4 or 3), else 0
   const float* centroid;    // [D]
   const uint32_t* chunk_off;  // [n_chunks+1]
   uint32_t D;               // dims of the index
@@ -411,10 +411,10 @@ __device__ __forceinline__ void build_pq_table(const SearchArgs& a, const float*
 
 // One table entry on demand: the identical operation sequence as build_pq_table for (chunk c, centre `code`),
 // reading the pivot row from the CTA-shared table — hence bit-identical to the reference's tbl[c][code].
-template <bool CHUNK4>
+template <int CS>  // CS = uniform chunk size known at compile time (4: 16-byte loads; 3), or 0 = read the chunk offsets
 __device__ __forceinline__ float adc_entry(const QState& s, uint32_t D, uint32_t c, uint32_t code) {
   float acc = 0.0f;
-  if (CHUNK4) {
+  if (CS == 4) {
     // 32-bit shared-space addresses, one 16-byte load each for the pivot row slice and the query residual
     const uint32_t pa = (uint32_t)__cvta_generic_to_shared(s.piv_s) + (code * D + 4u * c) * 4u;
     const uint32_t qa = (uint32_t)__cvta_generic_to_shared(s.qc) + 16u * c;
@@ -426,6 +426,11 @@ __device__ __forceinline__ float adc_entry(const QState& s, uint32_t D, uint32_t
     d = __fsub_rn(pv.y, qv.y); acc = __fmaf_rn(d, d, acc);
     d = __fsub_rn(pv.z, qv.z); acc = __fmaf_rn(d, d, acc);
     d = __fsub_rn(pv.w, qv.w); acc = __fmaf_rn(d, d, acc);
+  } else if (CS > 0) {
+    const float* p = s.piv_s + (size_t)code * D + CS * c;
+    const float* qv = s.qc + CS * c;
+#pragma unroll
+    for (int j = 0; j < CS; ++j) { const float d = __fsub_rn(p[j], qv[j]); acc = __fmaf_rn(d, d, acc); }
   } else {
     const float* p = s.piv_s + (size_t)code * D;
     const uint32_t j0 = s.coff_s[c], j1 = s.coff_s[c + 1];
@@ -436,13 +441,13 @@ __device__ __forceinline__ float adc_entry(const QState& s, uint32_t D, uint32_t
 
 // partial ADC sum of one 32-chunk group for lane t: chunks base+t, base+t+8, base+t+16, base+t+24 (ascending).
 // FULL: the group is known to be complete (n_chunks is a multiple of 32), no bounds checks.
-template <bool CHUNK4, bool FULL>
+template <int CS, bool FULL>
 __device__ __forceinline__ float adc_group(const QState& s, const SearchArgs& a, uint32_t word, uint32_t base, uint32_t t, float sum) {
   float e[4];
 #pragma unroll
   for (int b = 0; b < 4; ++b) {  // four independent chains, then the ordered sum
     const uint32_t c = base + t + 8 * b;
-    e[b] = (FULL || c < a.n_chunks) ? adc_entry<CHUNK4>(s, a.D, c, (word >> (8 * b)) & 0xff) : 0.0f;
+    e[b] = (FULL || c < a.n_chunks) ? adc_entry<CS>(s, a.D, c, (word >> (8 * b)) & 0xff) : 0.0f;
   }
 #pragma unroll
   for (int b = 0; b < 4; ++b)
@@ -506,7 +511,7 @@ __device__ __forceinline__ VisPos vis_pos(uint32_t id) {
 //   exact    compute_neighborDist_par                 BANG_Exactdistance/parANN.cu:1139-1179
 // Returns the number of accepted candidates; n_id/n_d hold them unordered; *deg_out = degree of the node.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE, bool CHUNK4>
+template <typename T, int MODE, int CS>
 __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* vis, uint2 nb2, bool first,
                                            uint32_t* deg_out, Prof& pf) {
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
@@ -605,7 +610,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       for (int p = 0; p < 4; ++p) {
         if (k0 + p * 4 < n) {  // warp-uniform
           const uint32_t k = k0 + p * 4 + g;
-          const float part = full32 ? adc_group<CHUNK4, true>(s, a, w[p], 0, t, 0.0f) : adc_group<CHUNK4, false>(s, a, w[p], 0, t, 0.0f);
+          const float part = full32 ? adc_group<CS, true>(s, a, w[p], 0, t, 0.0f) : adc_group<CS, false>(s, a, w[p], 0, t, 0.0f);
           const float sum = tree8(part);
           if (t == 0 && k < n) s.n_d[k] = sum;
         }
@@ -620,8 +625,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       for (uint32_t gg = 0; gg < groups; gg += 2) {
         const uint32_t wa = ld_nc_u32(row + gg * 32, s.pol_stream);
         const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32, s.pol_stream) : 0u;
-        sum = adc_group<CHUNK4, false>(s, a, wa, gg * 32, t, sum);
-        sum = adc_group<CHUNK4, false>(s, a, wb, (gg + 1) * 32, t, sum);
+        sum = adc_group<CS, false>(s, a, wa, gg * 32, t, sum);
+        sum = adc_group<CS, false>(s, a, wb, (gg + 1) * 32, t, sum);
       }
       sum = tree8(sum);
       if (t == 0 && k < n) s.n_d[k] = sum;
@@ -841,8 +846,8 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
 // ------------------------------------------------------------------------------------------------
 // the kernel: blockDim.x = 32 * (query warps per CTA)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE, bool CHUNK4>
-__global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const SearchArgs a) {
+template <typename T, int MODE, int CS>
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (CS == 0 ? 1 : 0)) bang_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   if (MODE != kExact) {
@@ -899,7 +904,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
-      uint32_t n = expand<T, MODE, CHUNK4>(a, s, vis, my_nb, true, &deg, pf);
+      uint32_t n = expand<T, MODE, CS>(a, s, vis, my_nb, true, &deg, pf);
       sum_deg += deg; n_pass += n;
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
@@ -916,7 +921,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
         n = 0;
-        if (have) { n = expand<T, MODE, CHUNK4>(a, s, vis, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
+        if (have) { n = expand<T, MODE, CS>(a, s, vis, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
@@ -945,7 +950,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32) bang_search_kernel(const
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-        const uint32_t n = expand<T, MODE, CHUNK4>(a, s, vis, my_nb, first, &deg, pf);
+        const uint32_t n = expand<T, MODE, CS>(a, s, vis, my_nb, first, &deg, pf);
         sum_deg += deg; n_pass += n;
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
         const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
