@@ -30,7 +30,8 @@ NO_ID = 0xFFFFFFFF
 # every symbol include/bang_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "bang_b200_create", "bang_b200_destroy", "bang_b200_load", "bang_b200_load_files", "bang_b200_set_sharding",
-    "bang_b200_export_shard", "bang_b200_import_shard", "bang_b200_set_searchparams", "bang_b200_alloc",
+    "bang_b200_export_shard", "bang_b200_import_shard", "bang_b200_load_device_begin", "bang_b200_load_device_rows",
+    "bang_b200_load_device_codes", "bang_b200_load_device_end", "bang_b200_set_searchparams", "bang_b200_alloc",
     "bang_b200_init", "bang_b200_query", "bang_b200_free", "bang_b200_unload", "bang_b200_set_dists_layout",
     "bang_b200_query_device", "bang_b200_pq_table", "bang_b200_info", "bang_b200_last_stats",
     "bang_b200_last_timing", "bang_b200_last_error", "bang_load_c", "bang_set_searchparams_c", "bang_query_c",
@@ -78,6 +79,10 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         "bang_b200_set_sharding": (ci, [vp, ci, ci]),
         "bang_b200_export_shard": (ci, [vp, vp]),
         "bang_b200_import_shard": (ci, [vp, ci, vp]),
+        "bang_b200_load_device_begin": (ci, [vp, u64, u32, u64, u32, vp, vp, vp]),
+        "bang_b200_load_device_rows": (ci, [vp, u64, u64, vp, vp]),
+        "bang_b200_load_device_codes": (ci, [vp, u64, u64, vp]),
+        "bang_b200_load_device_end": (ci, [vp]),
         "bang_b200_set_searchparams": (ci, [vp, ci, ci, ci]),
         "bang_b200_alloc": (ci, [vp, ci]),
         "bang_b200_init": (ci, [vp, ci]),
@@ -198,6 +203,23 @@ class BANGSearch:
     def import_shard(self, shard: int, handle: bytes) -> None:
         buf = ctypes.create_string_buffer(handle, 64)
         self._check(self._lib.bang_b200_import_shard(self._h, shard, buf))
+
+    # device-resident load (indices built on the GPUs, too large for files)
+    def load_device_begin(self, N: int, D: int, medoid: int, pivots=None, centroid=None, chunk_offsets=None) -> None:
+        m = 0 if chunk_offsets is None else len(chunk_offsets) - 1
+        keep = [None if a is None else np.ascontiguousarray(a, dtype=dt) for a, dt in
+                ((pivots, np.float32), (centroid, np.float32), (chunk_offsets, np.uint32))]
+        ptr = lambda a: None if a is None else a.ctypes.data
+        self._check(self._lib.bang_b200_load_device_begin(self._h, N, D, medoid, m, ptr(keep[0]), ptr(keep[1]), ptr(keep[2])))
+
+    def load_device_rows(self, first_local_row: int, n_rows: int, d_vectors_ptr: int, d_adj_ptr: int) -> None:
+        self._check(self._lib.bang_b200_load_device_rows(self._h, first_local_row, n_rows, d_vectors_ptr, d_adj_ptr))
+
+    def load_device_codes(self, first_id: int, n: int, d_codes_ptr: int) -> None:
+        self._check(self._lib.bang_b200_load_device_codes(self._h, first_id, n, d_codes_ptr))
+
+    def load_device_end(self) -> None:
+        self._check(self._lib.bang_b200_load_device_end(self._h))
 
     def query_device(self, d_queries_ptr: int, Q: int, d_ids_ptr: int, d_dists_ptr: int, stream: int = 0) -> None:
         self._check(self._lib.bang_b200_query_device(self._h, d_queries_ptr, Q, d_ids_ptr, d_dists_ptr, stream))

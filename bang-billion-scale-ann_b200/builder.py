@@ -60,8 +60,9 @@ def make_fixture(prefix: str, n: int, d: int, dtype: str, nq: int, m: int | None
 
 
 def build_vamana_gpu(base: torch.Tensor, medoid: int, L: int = 64, alpha: float = 1.2, passes: int = 2, seed: int = 1,
-                     max_batch: int = 0):
-    """Batch-parallel Vamana on the GPU (csrc/builder.cu).  base: CUDA tensor [N][D] uint8/int8/float32."""
+                     max_batch: int = 0, device_out: bool = False):
+    """Batch-parallel Vamana on the GPU (csrc/builder.cu).  base: CUDA tensor [N][D] uint8/int8/float32.
+    device_out: return the adjacency as a CUDA int32 tensor [N][64] (unused = -1) instead of host arrays."""
     assert base.is_cuda and base.is_contiguous()
     lib = ctypes.CDLL(_build.build_cuda())
     fn = lib.bang_b200_build_vamana
@@ -76,10 +77,18 @@ def build_vamana_gpu(base: torch.Tensor, medoid: int, L: int = 64, alpha: float 
     g.manual_seed(seed)
     order = torch.cat([torch.randperm(N, generator=g, device=base.device) for _ in range(passes)]).to(torch.int32).contiguous()
     n_first = N if passes > 1 else 0
-    deg = np.zeros(N, dtype=np.uint32)
-    nbrs = np.zeros((N, 64), dtype=np.uint32)
     stats = np.zeros(4, dtype=np.float32)
     torch.cuda.synchronize(base.device)
+    if device_out:
+        d_nbrs = torch.empty((N, 64), dtype=torch.int32, device=base.device)
+        with torch.cuda.device(base.device):
+            rc = fn(_DT[dt], base.data_ptr(), N, D, L, 1.0, n_first, alpha, order.data_ptr(), order.numel(), medoid,
+                    (max_batch & 0x7FFFFFFF) | 0x80000000, None, d_nbrs.data_ptr(), stats.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("bang_b200_build_vamana: " + lib.bang_b200_builder_last_error().decode())
+        return d_nbrs
+    deg = np.zeros(N, dtype=np.uint32)
+    nbrs = np.zeros((N, 64), dtype=np.uint32)
     with torch.cuda.device(base.device):
         rc = fn(_DT[dt], base.data_ptr(), N, D, L, 1.0, n_first, alpha, order.data_ptr(), order.numel(), medoid, max_batch,
                 deg.ctypes.data, nbrs.ctypes.data, stats.ctypes.data)

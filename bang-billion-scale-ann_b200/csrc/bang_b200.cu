@@ -62,6 +62,17 @@ __global__ void repack_codes_kernel(const uint8_t* __restrict__ src, uint32_t m,
   dst[row * code_stride + p] = c < m ? src[row * m + c] : (uint8_t)0;
 }
 
+// device arrays -> HBM rows (bang_b200_load_device_rows): one warp per node
+__global__ void pack_rows_kernel(const uint8_t* __restrict__ vec, uint32_t vec_bytes, const uint32_t* __restrict__ adj,
+                                 uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t n) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  uint8_t* d = dst + warp * (uint64_t)row_stride;
+  for (uint32_t i = lane; i < (uint32_t)kMaxR; i += 32) reinterpret_cast<uint32_t*>(d)[i] = adj[warp * kMaxR + i];
+  for (uint32_t i = lane; i < row_stride - kAdjBytes; i += 32) d[kAdjBytes + i] = i < vec_bytes ? vec[warp * vec_bytes + i] : (uint8_t)0;
+}
+
 }  // namespace bang
 
 static thread_local std::string g_err;
@@ -384,6 +395,83 @@ extern "C" int bang_b200_load_files(bang_handle_t c, const char* pq_pivots_bin, 
     if (rc != BANG_OK) return finish_load(c, rc);
   }
   return finish_load(c, load_graph(c, disk_bin));
+}
+
+// ---- device-resident load ---------------------------------------------------------------------
+extern "C" int bang_b200_load_device_begin(bang_handle_t c, uint64_t N, uint32_t D, uint64_t medoid, uint32_t n_chunks,
+                                           const float* pivots, const float* centroid, const uint32_t* chunk_offsets) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (c->loaded) return set_err(BANG_E_STATE, "index already loaded");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->N = N; c->D = D; c->R = kMaxR; c->medoid = medoid;
+  c->entry_len = (uint64_t)D * elem_size(c->dtype) + 4 + 4ull * kMaxR;
+  c->device_bytes = 0;
+  int rc = check_common(c);
+  if (rc != BANG_OK) return rc;
+  c->loaded = true;  // from here on bang_b200_unload releases whatever was allocated
+  if (c->mode != BANG_MODE_EXACTDISTANCE) {
+    if (!pivots || !centroid || !chunk_offsets || n_chunks == 0) { bang_b200_unload(c); return set_err(BANG_E_ARG, "PQ arrays are required in Base/Inmemory mode"); }
+    c->n_chunks = n_chunks;
+    c->code_stride = (n_chunks + 31) / 32 * 32;
+    PQHost pq;
+    pq.pivots.assign(pivots, pivots + (size_t)256 * D);
+    pq.centroid.assign(centroid, centroid + D);
+    pq.chunk_off.assign(chunk_offsets, chunk_offsets + n_chunks + 1);
+    rc = upload_pq(c, pq);
+    if (rc == BANG_OK) {
+      cudaError_t e = cudaMalloc(&c->d_codes, (size_t)N * c->code_stride);
+      if (e != cudaSuccess) rc = set_err(BANG_E_NOMEM, std::string("codes: ") + cudaGetErrorString(e));
+      else c->device_bytes += (size_t)N * c->code_stride;
+    }
+    if (rc != BANG_OK) { std::string k = g_err; bang_b200_unload(c); g_err = k; return rc; }
+  }
+  c->vec_bytes = D * (uint32_t)elem_size(c->dtype);
+  c->vec_units = (c->vec_bytes + 15) / 16;
+  c->row_stride = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
+  c->rows_local = (N + c->n_shards - 1 - c->shard) / c->n_shards;
+  const size_t bytes = (size_t)c->rows_local * c->row_stride;
+  cudaError_t e = cudaMalloc(&c->d_rows, std::max<size_t>(bytes, 256));
+  if (e != cudaSuccess) { bang_b200_unload(c); return set_err(BANG_E_NOMEM, std::string("rows: ") + cudaGetErrorString(e)); }
+  c->device_bytes += bytes;
+  for (int s = 0; s < kMaxShards; ++s) c->rows[s] = nullptr;
+  c->rows[c->shard] = c->d_rows;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_load_device_rows(bang_handle_t c, uint64_t first_local_row, uint64_t n_rows, const void* d_vectors,
+                                          const uint32_t* d_adj) {
+  if (!c || !d_vectors || !d_adj) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded || !c->d_rows) return set_err(BANG_E_STATE, "bang_b200_load_device_begin first");
+  if (first_local_row + n_rows > c->rows_local) return set_err(BANG_E_ARG, "row range exceeds this shard");
+  if (n_rows == 0) return BANG_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t threads = n_rows * 32;
+  pack_rows_kernel<<<(unsigned)((threads + 255) / 256), 256>>>((const uint8_t*)d_vectors, c->vec_bytes, d_adj,
+                                                             c->d_rows + first_local_row * c->row_stride, c->row_stride, n_rows);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_load_device_codes(bang_handle_t c, uint64_t first_id, uint64_t n, const uint8_t* d_codes) {
+  if (!c || !d_codes) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded || !c->d_codes) return set_err(BANG_E_STATE, "bang_b200_load_device_begin (PQ mode) first");
+  if (first_id + n > c->N) return set_err(BANG_E_ARG, "id range exceeds N");
+  if (n == 0) return BANG_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t total = n * c->code_stride;
+  repack_codes_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_codes, c->n_chunks, c->d_codes + first_id * c->code_stride,
+                                                                c->code_stride, n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_load_device_end(bang_handle_t c) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (!c->loaded || !c->d_rows) return set_err(BANG_E_STATE, "bang_b200_load_device_begin first");
+  CUDA_TRY(cudaDeviceSynchronize());
+  return BANG_OK;
 }
 
 extern "C" int bang_b200_unload(bang_handle_t c) {

@@ -226,7 +226,7 @@ __global__ void gather_queries_kernel(const uint8_t* vec, uint32_t vec_bytes, co
 
 // final: per node, neighbour ids ascending (bang_preprocess.py:102-104), degree, and a fallback edge for isolated nodes
 __global__ void finalize_kernel(const uint8_t* rows, uint32_t row_stride, uint64_t N, uint32_t medoid, uint32_t* deg_out,
-                                uint32_t* nbr_out) {
+                                uint32_t* nbr_out, uint32_t pad_value) {
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (warp >= N) return;
@@ -243,16 +243,12 @@ __global__ void finalize_kernel(const uint8_t* rows, uint32_t row_stride, uint64
   }
   uint32_t* out = nbr_out + warp * kMaxR;
   const uint32_t d = __popc(__ballot_sync(0xffffffffu, a != kNoNbr)) + __popc(__ballot_sync(0xffffffffu, b != kNoNbr));
-  out[ra] = a == kNoNbr ? 0u : a;
-  out[rb] = b == kNoNbr ? 0u : b;
+  out[ra] = a == kNoNbr ? pad_value : a;
+  out[rb] = b == kNoNbr ? pad_value : b;
   __syncwarp();
   if (lane == 0) {
-    if (d == 0) {
-      out[0] = (uint32_t)warp == medoid ? (uint32_t)((medoid + 1) % N) : medoid;
-      deg_out[warp] = 1;
-    } else {
-      deg_out[warp] = d;
-    }
+    if (d == 0) out[0] = (uint32_t)warp == medoid ? (uint32_t)((medoid + 1) % N) : medoid;
+    if (deg_out) deg_out[warp] = d == 0 ? 1u : d;
   }
 }
 
@@ -269,7 +265,7 @@ thread_local std::string b_err;
 template <typename T>
 int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float alpha_first, uint64_t n_first, float alpha_rest,
                const uint32_t* d_order, uint64_t n_order, uint32_t medoid, uint32_t max_batch, uint32_t* h_deg, uint32_t* h_nbrs,
-               float* stats_out) {
+               float* stats_out, bool device_out) {
   const uint32_t vec_bytes = D * sizeof(T);
   const uint32_t vec_units = (vec_bytes + 15) / 16;
   const uint32_t row_stride = (uint32_t)align_up(kAdjBytes + (size_t)vec_units * 16, 32);
@@ -353,17 +349,27 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
     if (bs < MB) bs = std::min<uint32_t>(MB, bs * 2);
   }
   B_TRY(cudaDeviceSynchronize());
-  uint32_t *d_deg = nullptr, *d_nbr = nullptr;
-  B_TRY(cudaMalloc(&d_deg, N * 4));
-  B_TRY(cudaMalloc(&d_nbr, N * kMaxR * 4));
-  finalize_kernel<<<(unsigned)((N * 32 + 255) / 256), 256>>>(rows, row_stride, N, medoid, d_deg, d_nbr);
-  B_TRY(cudaGetLastError());
-  B_TRY(cudaMemcpy(h_deg, d_deg, N * 4, cudaMemcpyDeviceToHost));
-  B_TRY(cudaMemcpy(h_nbrs, d_nbr, N * kMaxR * 4, cudaMemcpyDeviceToHost));
-  if (stats_out) stats_out[0] = (float)n_batches;
-  cudaFree(d_deg); cudaFree(d_nbr); cudaFree(rows); cudaFree(d_q); cudaFree(d_ids); cudaFree(d_dd); cudaFree(d_bloom); cudaFree(d_counter);
+  // the per-batch scratch is no longer needed: release it before the outputs are materialised
+  cudaFree(d_q); cudaFree(d_ids); cudaFree(d_dd); cudaFree(d_bloom); cudaFree(d_counter);
   cudaFree(d_dump); cudaFree(d_dump_n); cudaFree(d_dst); cudaFree(d_src); cudaFree(d_dst2); cudaFree(d_src2); cudaFree(d_seg);
   cudaFree(d_segc); cudaFree(d_tmp);
+  if (device_out) {
+    // outputs are DEVICE arrays: neighbours ascending, unused slots 0xFFFFFFFF (the search kernel's padding)
+    finalize_kernel<<<(unsigned)((N * 32 + 255) / 256), 256>>>(rows, row_stride, N, medoid, h_deg, h_nbrs, kNoNbr);
+    B_TRY(cudaGetLastError());
+    B_TRY(cudaDeviceSynchronize());
+  } else {
+    uint32_t *d_deg = nullptr, *d_nbr = nullptr;
+    B_TRY(cudaMalloc(&d_deg, N * 4));
+    B_TRY(cudaMalloc(&d_nbr, N * kMaxR * 4));
+    finalize_kernel<<<(unsigned)((N * 32 + 255) / 256), 256>>>(rows, row_stride, N, medoid, d_deg, d_nbr, 0u);
+    B_TRY(cudaGetLastError());
+    B_TRY(cudaMemcpy(h_deg, d_deg, N * 4, cudaMemcpyDeviceToHost));
+    B_TRY(cudaMemcpy(h_nbrs, d_nbr, N * kMaxR * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_deg); cudaFree(d_nbr);
+  }
+  if (stats_out) stats_out[0] = (float)n_batches;
+  cudaFree(rows);
   return BANG_OK;
 }
 
@@ -377,11 +383,14 @@ extern "C" const char* bang_b200_builder_last_error(void) { return b_err.c_str()
 extern "C" int bang_b200_build_vamana(int dtype, const void* d_vectors, uint64_t N, uint32_t D, uint32_t L_build, float alpha_first,
                                       uint64_t n_first, float alpha_rest, const uint32_t* d_order, uint64_t n_order, uint64_t medoid,
                                       uint32_t max_batch, uint32_t* h_deg, uint32_t* h_nbrs, float* stats_out) {
-  if (!d_vectors || !d_order || !h_deg || !h_nbrs || N < 2 || medoid >= N) { b_err = "bad argument"; return BANG_E_ARG; }
+  // max_batch bit 31: the outputs are DEVICE arrays (h_deg may then be null; unused neighbour slots = 0xFFFFFFFF)
+  const bool device_out = (max_batch & 0x80000000u) != 0;
+  max_batch &= 0x7FFFFFFFu;
+  if (!d_vectors || !d_order || (!h_deg && !device_out) || !h_nbrs || N < 2 || medoid >= N) { b_err = "bad argument"; return BANG_E_ARG; }
   switch (dtype) {
-    case BANG_DT_FLOAT: return build_impl<float>(d_vectors, N, D, L_build, alpha_first, n_first, alpha_rest, d_order, n_order, (uint32_t)medoid, max_batch, h_deg, h_nbrs, stats_out);
-    case BANG_DT_INT8: return build_impl<int8_t>(d_vectors, N, D, L_build, alpha_first, n_first, alpha_rest, d_order, n_order, (uint32_t)medoid, max_batch, h_deg, h_nbrs, stats_out);
-    case BANG_DT_UINT8: return build_impl<uint8_t>(d_vectors, N, D, L_build, alpha_first, n_first, alpha_rest, d_order, n_order, (uint32_t)medoid, max_batch, h_deg, h_nbrs, stats_out);
+    case BANG_DT_FLOAT: return build_impl<float>(d_vectors, N, D, L_build, alpha_first, n_first, alpha_rest, d_order, n_order, (uint32_t)medoid, max_batch, h_deg, h_nbrs, stats_out, device_out);
+    case BANG_DT_INT8: return build_impl<int8_t>(d_vectors, N, D, L_build, alpha_first, n_first, alpha_rest, d_order, n_order, (uint32_t)medoid, max_batch, h_deg, h_nbrs, stats_out, device_out);
+    case BANG_DT_UINT8: return build_impl<uint8_t>(d_vectors, N, D, L_build, alpha_first, n_first, alpha_rest, d_order, n_order, (uint32_t)medoid, max_batch, h_deg, h_nbrs, stats_out, device_out);
   }
   b_err = "bad dtype";
   return BANG_E_ARG;

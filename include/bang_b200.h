@@ -72,6 +72,18 @@ int bang_b200_set_sharding(bang_handle_t h, int shard, int n_shards);
 int bang_b200_export_shard(bang_handle_t h, void* ipc_handle_64B);
 int bang_b200_import_shard(bang_handle_t h, int shard, const void* ipc_handle_64B);
 
+/* Device-resident load (no files): for indices that are built on the GPUs themselves and are too large for the
+ * box's disk (SIFT1B-shape: a 388 GB `_disk.bin`).  Same HBM layout and search as bang_b200_load; honours
+ * bang_b200_set_sharding (local row r of shard s holds node r * n_shards + s).  begin -> rows* -> codes* -> end.
+ * pivots/centroid/chunk_offsets are HOST arrays in the file's order (float[256][D], float[D], u32[n_chunks+1]);
+ * d_vectors (T[n][D]), d_adj (u32[n][64], unused slots 0xFFFFFFFF) and d_codes (u8[n][n_chunks]) are DEVICE arrays. */
+int bang_b200_load_device_begin(bang_handle_t h, uint64_t N, uint32_t D, uint64_t medoid, uint32_t n_chunks,
+                                const float* pivots, const float* centroid, const uint32_t* chunk_offsets);
+int bang_b200_load_device_rows(bang_handle_t h, uint64_t first_local_row, uint64_t n_rows, const void* d_vectors,
+                               const uint32_t* d_adj);
+int bang_b200_load_device_codes(bang_handle_t h, uint64_t first_id, uint64_t n, const uint8_t* d_codes);
+int bang_b200_load_device_end(bang_handle_t h);
+
 /* BANGSearch<T>::bang_set_searchparams (bang.h:60-62, bang_search.cu:562-567) */
 int bang_b200_set_searchparams(bang_handle_t h, int recall, int worklist_length, bang_distfn_t dist);
 /* BANGSearch<T>::bang_alloc (bang.h:55, bang_search.cu:367-423) */

@@ -15,7 +15,9 @@ extern "C" {
 /* d_vectors: DEVICE T[N][D] (dtype as bang_dtype_t); d_order: DEVICE u32[n_order] insertion order (ids may
  * repeat for a second pass); the first n_first insertions prune with alpha_first, the rest with alpha_rest;
  * medoid: entry point of every search; max_batch 0 = min(max(N/50,1024),65536).
- * Outputs (HOST): h_deg u32[N] in [1,64]; h_nbrs u32[N][64], first h_deg[i] ids ascending, rest 0. */
+ * Outputs (HOST): h_deg u32[N] in [1,64]; h_nbrs u32[N][64], first h_deg[i] ids ascending, rest 0.
+ * With bit 31 of max_batch set the outputs are DEVICE arrays instead (h_deg may be NULL) and unused neighbour
+ * slots hold 0xFFFFFFFF — the form bang_b200_load_device_rows consumes. */
 int bang_b200_build_vamana(int dtype, const void* d_vectors, uint64_t N, uint32_t D, uint32_t L_build, float alpha_first,
                            uint64_t n_first, float alpha_rest, const uint32_t* d_order, uint64_t n_order, uint64_t medoid,
                            uint32_t max_batch, uint32_t* h_deg, uint32_t* h_nbrs, float* stats_out);

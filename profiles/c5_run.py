@@ -1,0 +1,67 @@
+"""C5 SIFT1B-shape: graph rows sharded id % G over the GPUs' HBM, PQ codes replicated, P2P neighbour fetch in the
+traversal kernel (replaces BANG_Base's host-RAM graph + PCIe fetch).  Index built on the GPUs (build_sharded.py).
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29551 profiles/c5_run.py N [Q] [Ls]
+Prints one JSON line per worklist length from rank 0 and writes them to gpurun_out/c5_<N>.jsonl"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch, torch.distributed as dist
+import bang_b200
+from bang_b200 import api, build_sharded, recall, sharding
+
+N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 4_000_000
+Q = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
+Ls = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [64, 128, 176, 256]
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+t_all = time.time()
+s = api.BANGSearch("uint8", "inmemory", device=local)
+s.set_sharding(rank, world)
+n_gt = min(1000, Q)
+my_q, gt_ids, gt_d, medoid, T = build_sharded.build_and_load(s, N, 128, Q, n_gt, P_per_rank=int(os.environ.get("C5_SHARDS_PER_RANK", "4")),
+                                                             passes=int(os.environ.get("C5_PASSES", "2")))
+sharding.exchange_shards(s, rank, world)
+info = s.info()
+if rank == 0:
+    print(f"[c5] N={N} built+loaded in {time.time() - t_all:.1f}s {T}; per-GPU HBM {info.device_bytes / 2**30:.1f} GiB; medoid {medoid}", flush=True)
+s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+out = []
+for L in Ls:
+    s.bang_set_searchparams(10, L)
+    s.bang_alloc(Q)
+    ms, e2e = [], []
+    for r in range(5):
+        s.bang_init(Q)
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ids, d = s.bang_query(my_q)
+        e2e.append((time.perf_counter() - t0) * 1e3)
+        ms.append(s.last_timing().kernel_ms)
+    st = s.last_stats(Q)
+    k_ms = sharding.max_over_ranks([float(np.mean(ms[2:]))], device=torch.device("cuda", local))[0]
+    e_ms = sharding.max_over_ranks([float(np.mean(e2e[2:]))], device=torch.device("cuda", local))[0]
+    esz = 1
+    bq = api.algorithmic_bytes(st, "inmemory", 128, esz, 32, 10)
+    adj_vec = 4 * st["hops"].astype(np.int64) + 4 * st["sum_deg"].astype(np.int64) + st["hops"].astype(np.int64) * 128
+    nvlink = adj_vec * (world - 1) / world
+    if rank == 0:
+        rec = recall.calculate_recall(gt_ids[:n_gt], gt_d[:n_gt], ids[:n_gt], 10)
+        line = {"metric": "QPS at recall@10 (batched greedy Vamana search, SIFT1B-shape, graph sharded over HBM)", "n_gpus": world,
+                "N": N, "L": L, "recall_at_10": round(rec, 2), "recall_queries": n_gt, "kernel_ms_max_over_ranks": k_ms,
+                "value": world * Q / (k_ms * 1e-3), "e2e": world * Q / (e_ms * 1e-3), "unit": "QPS",
+                "queries_per_gpu": Q, "hops_per_query": float(st["hops"].mean()), "candidates_per_query": float(st["n_cand"].mean()),
+                "bytes_per_query": float(bq.mean()), "nvlink_bytes_per_query": float(nvlink.mean()),
+                "per_gpu_hbm_gib": info.device_bytes / 2**30, "build_seconds": T}
+        print(json.dumps(line), flush=True)
+        out.append(line)
+    s.bang_free()
+dist.barrier()
+if rank == 0:
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"c5_{N}.jsonl"), "w") as f:
+        for l in out:
+            f.write(json.dumps(l) + "\n")
+s.bang_unload()
+dist.barrier()
+dist.destroy_process_group()
