@@ -58,21 +58,31 @@ def _hash32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def merge_lists(adj_own: torch.Tensor, rows: torch.Tensor, new: torch.Tensor, gid_of_row_mul: int, gid_of_row_add: int) -> None:
-    """adj_own[rows] <- the 64 smallest-hash members of (adj_own[rows] ∪ new), rows unique within the call."""
+    """adj_own[rows] <- the 64 smallest-hash members of (adj_own[rows] ∪ new); rows unique within the call.
+    Rows that are still empty (the first of a node's two copies) just take the list."""
+    rows = rows.long()
+    empty = adj_own[rows, 0] < 0
+    if bool(empty.any()):
+        adj_own[rows[empty]] = new[empty]
+    if bool(empty.all()):
+        return
+    rows, new = rows[~empty], new[~empty]
     step = 1 << 20
     for s in range(0, rows.numel(), step):
-        r = rows[s:s + step].long()
-        cat = torch.cat([adj_own[r], new[s:s + step]], 1).long()             # [m,128], -1 = empty
+        r = rows[s:s + step]
+        cat = torch.cat([adj_own[r], new[s:s + step]], 1)                    # int32 [m,128], -1 = empty
         cat, _ = torch.sort(cat, dim=1)
         dup = torch.zeros_like(cat, dtype=torch.bool)
         dup[:, 1:] = cat[:, 1:] == cat[:, :-1]
         v = (r * gid_of_row_mul + gid_of_row_add)[:, None]
-        h = _hash32(v.expand_as(cat), cat)
-        h = torch.where((cat < 0) | dup | (cat == v), torch.full_like(h, 1 << 40), h)
+        catl = cat.long()
+        h = _hash32(v.expand_as(catl), catl)
+        h = torch.where((cat < 0) | dup | (catl == v), torch.full_like(h, 1 << 40), h)
         hs, idx = torch.topk(h, 64, dim=1, largest=False)
         out = torch.gather(cat, 1, idx)
         out = torch.where(hs >= (1 << 40), torch.full_like(out, -1), out)
-        adj_own[r] = out.to(torch.int32)
+        adj_own[r] = out
+        del cat, catl, dup, h, hs, idx, out
 
 
 def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries: int, m: int = 32, P_per_rank: int = 4,
@@ -187,7 +197,10 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
         t0 = time.time()
         ns = sh_n[j]
         vec = sh_vec[j][:ns]
-        loc_med = int(((vec[:: max(1, ns // 65536)].float() - vec.float().mean(0)) ** 2).sum(1).argmin()) * max(1, ns // 65536)
+        stride = max(1, ns // 65536)
+        sample = vec[::stride].float()
+        loc_med = int(((sample - sample.mean(0)) ** 2).sum(1).argmin()) * stride   # entry point of the shard graph
+        del sample
         nb = build_vamana_gpu(vec, min(loc_med, ns - 1), L=L_build, passes=passes, seed=s + 1, device_out=True)   # int32 [ns][64] local ids
         gidt = sh_gid[j][:ns]
         sh_vec[j] = None
