@@ -86,6 +86,8 @@ def build_vamana_gpu(base: torch.Tensor, medoid: int, L: int = 64, alpha: float 
                     (max_batch & 0x7FFFFFFF) | 0x80000000, None, d_nbrs.data_ptr(), stats.ctypes.data)
         if rc != 0:
             raise RuntimeError("bang_b200_build_vamana: " + lib.bang_b200_builder_last_error().decode())
+        if os.environ.get("BANG_B200_BUILD_TIMERS"):
+            print("[builder] batches %d search %.0f ms prune %.0f ms reverse %.0f ms" % tuple(stats.tolist()), flush=True)
         return d_nbrs
     deg = np.zeros(N, dtype=np.uint32)
     nbrs = np.zeros((N, 64), dtype=np.uint32)

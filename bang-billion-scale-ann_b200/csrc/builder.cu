@@ -9,10 +9,10 @@
 // re-prune on overflow.  Batches double in size up to 2 % of N so early points see a dense graph.
 // The graph lives in the search kernel's own HBM row layout while it is built.
 #include <cuda_runtime.h>
-#include <cub/cub.cuh>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -101,6 +101,7 @@ __device__ void robust_prune(uint8_t* rows, uint32_t row_stride, uint32_t vec_un
   uint32_t* adj = reinterpret_cast<uint32_t*>(rows + (size_t)p * row_stride);
   __syncthreads();
   for (uint32_t i = tid; i < (uint32_t)kMaxR; i += kPruneThreads) adj[i] = i < cnt ? sel[i] : kNoNbr;
+  if (tid == 0) scal[1] = cnt;  // number of neighbours kept
 }
 
 struct PruneSmem {
@@ -117,7 +118,8 @@ struct PruneSmem {
 template <typename T>
 __global__ void __launch_bounds__(kPruneThreads) prune_batch_kernel(uint8_t* rows, uint32_t row_stride, uint32_t vec_units,
                                                                     const uint32_t* batch_ids, uint32_t B, const uint32_t* dump_ids,
-                                                                    const uint32_t* dump_n, uint32_t dump_stride, float alpha) {
+                                                                    const uint32_t* dump_n, uint32_t dump_stride, float alpha,
+                                                                    uint32_t* deg_arr, const uint32_t* ovf, uint32_t* ovf_cnt) {
   extern __shared__ __align__(16) uint8_t raw[];
   PruneSmem* sm = reinterpret_cast<PruneSmem*>(raw);
   float* pv = reinterpret_cast<float*>(raw + align_up(sizeof(PruneSmem), 16));
@@ -125,86 +127,80 @@ __global__ void __launch_bounds__(kPruneThreads) prune_batch_kernel(uint8_t* row
   if (b >= B) return;
   const uint32_t p = batch_ids[b];
   const uint32_t tid = threadIdx.x;
-  uint32_t nv = min(dump_n[b], (uint32_t)(kMaxCand - kMaxR));
+  const uint32_t extra = min(ovf_cnt[p], 32u);  // pending reverse edges of p (kSlack)
+  uint32_t nv = min(dump_n[b], (uint32_t)(kMaxCand - kMaxR - 32));
   for (uint32_t i = tid; i < nv; i += kPruneThreads) sm->c_id[i] = dump_ids[(size_t)b * dump_stride + i];
   const uint32_t* adj = reinterpret_cast<const uint32_t*>(rows + (size_t)p * row_stride);
   uint32_t mine = kNoNbr;
   if (tid < kMaxR) mine = adj[tid];
   const uint32_t deg = __syncthreads_count(tid < kMaxR && mine != kNoNbr);
   if (tid < kMaxR && mine != kNoNbr) sm->c_id[nv + tid] = mine;  // valid entries are the leading ones
+  if (tid < extra) sm->c_id[nv + deg + tid] = ovf[(size_t)p * 32 + tid];
   __syncthreads();
-  robust_prune<T>(rows, row_stride, vec_units, p, nv + deg, alpha, sm->c_id, sm->c_d, sm->s_id, sm->s_d, sm->dead, pv, sm->sel,
+  robust_prune<T>(rows, row_stride, vec_units, p, nv + deg + extra, alpha, sm->c_id, sm->c_d, sm->s_id, sm->s_d, sm->dead, pv, sm->sel,
                   sm->scal);
+  __syncthreads();
+  if (tid == 0) { deg_arr[p] = sm->scal[1]; ovf_cnt[p] = 0; }
 }
 
-// phase 2a: emit (dst = neighbour, src = batch point) pairs
-__global__ void emit_reverse_kernel(const uint8_t* rows, uint32_t row_stride, const uint32_t* batch_ids, uint32_t B,
-                                    uint32_t* dst, uint32_t* src) {
+// ---- reverse edges with slack (DiskANN keeps up to 1.3 R edges before it re-prunes a node) ---------------------
+// A node's row holds at most 64 neighbours; reverse edges that do not fit wait in a 32-entry side list and the
+// node is re-pruned over (row ∪ side list) only when that list fills up, i.e. once per 32 insertions instead of
+// once per insertion.  deg[j] counts the row's valid slots (values > 64 mean "row full").
+constexpr int kSlack = 32;
+
+// phase 2a: one thread per new edge p -> j: append p to j's row if it has room, else to j's side list
+__global__ void reverse_append_kernel(uint8_t* rows, uint32_t row_stride, const uint32_t* batch_ids, uint32_t B, uint32_t* deg,
+                                      uint32_t* ovf, uint32_t* ovf_cnt, uint32_t* prune_list, uint32_t* prune_n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kMaxR) return;
-  const uint32_t b = i / kMaxR, s = i % kMaxR;
-  const uint32_t p = batch_ids[b];
-  const uint32_t nb = reinterpret_cast<const uint32_t*>(rows + (size_t)p * row_stride)[s];
-  dst[i] = nb;  // kNoNbr sorts last
-  src[i] = p;
+  const uint32_t p = batch_ids[i / kMaxR];
+  const uint32_t j = reinterpret_cast<const uint32_t*>(rows + (size_t)p * row_stride)[i % kMaxR];
+  if (j == kNoNbr || j == p) return;
+  uint32_t* adj = reinterpret_cast<uint32_t*>(rows + (size_t)j * row_stride);
+  const uint4* a4 = reinterpret_cast<const uint4*>(adj);
+  bool present = false;
+#pragma unroll 4
+  for (int k = 0; k < kMaxR / 4; ++k) {
+    const uint4 v = a4[k];
+    present |= v.x == p || v.y == p || v.z == p || v.w == p;
+  }
+  if (present) return;
+  const uint32_t old = atomicAdd(&deg[j], 1u);
+  if (old < (uint32_t)kMaxR) { adj[old] = p; return; }
+  const uint32_t slot = atomicAdd(&ovf_cnt[j], 1u);
+  if (slot < (uint32_t)kSlack) ovf[(size_t)j * kSlack + slot] = p;
+  if (slot == (uint32_t)kSlack - 1) prune_list[atomicAdd(prune_n, 1u)] = j;  // the list just filled up
 }
 
-// phase 2b: segment heads of the dst-sorted pair list
-__global__ void segment_heads_kernel(const uint32_t* dst, uint32_t n, uint32_t* seg_start, uint32_t* seg_count) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (dst[i] == kNoNbr) return;
-  if (i == 0 || dst[i] != dst[i - 1]) seg_start[atomicAdd(seg_count, 1u)] = i;
-}
-
-// phase 2c: one CTA per distinct destination j: append the incoming edges, or re-prune on overflow
+// phase 2b: re-prune the listed nodes over row ∪ side list (persistent grid; `all` = final flush over every node)
 template <typename T>
-__global__ void __launch_bounds__(kPruneThreads) reverse_insert_kernel(uint8_t* rows, uint32_t row_stride, uint32_t vec_units,
-                                                                       const uint32_t* dst, const uint32_t* src, uint32_t n_pairs,
-                                                                       const uint32_t* seg_start, const uint32_t* seg_count,
-                                                                       float alpha) {
+__global__ void __launch_bounds__(kPruneThreads) slack_prune_kernel(uint8_t* rows, uint32_t row_stride, uint32_t vec_units,
+                                                                    uint32_t* deg, const uint32_t* ovf, uint32_t* ovf_cnt,
+                                                                    const uint32_t* prune_list, const uint32_t* prune_n, uint64_t N,
+                                                                    bool all, float alpha) {
   extern __shared__ __align__(16) uint8_t raw[];
   PruneSmem* sm = reinterpret_cast<PruneSmem*>(raw);
   float* pv = reinterpret_cast<float*>(raw + align_up(sizeof(PruneSmem), 16));
-  if (blockIdx.x >= *seg_count) return;
   const uint32_t tid = threadIdx.x;
-  const uint32_t start = seg_start[blockIdx.x];
-  const uint32_t j = dst[start];
-  uint32_t* adj = reinterpret_cast<uint32_t*>(rows + (size_t)j * row_stride);
-  uint32_t mine = kNoNbr;
-  if (tid < kMaxR) mine = adj[tid];
-  const uint32_t deg = __syncthreads_count(tid < kMaxR && mine != kNoNbr);
-  if (tid < kMaxR && mine != kNoNbr) sm->c_id[tid] = mine;
-  __syncthreads();
-  // incoming sources not already present (the segment is short: scan it with the whole CTA)
-  if (tid == 0) sm->scal[1] = deg;
-  __syncthreads();
-  const uint32_t cap = kMaxCand - kMaxR;
-  for (uint32_t i0 = start; i0 < n_pairs; i0 += kPruneThreads) {
-    const uint32_t i = i0 + tid;
-    const bool in = i < n_pairs && dst[i] == j;
-    if (in) {
-      const uint32_t s = src[i];
-      bool present = (s == j);
-      for (uint32_t e = 0; e < deg && !present; ++e) present = sm->c_id[e] == s;
-      if (!present) {
-        const uint32_t pos = atomicAdd(&sm->scal[1], 1u);
-        if (pos < deg + cap) sm->c_id[pos] = s;
-      }
-    }
-    // stop after the last element of the segment (uniform decision)
-    const uint32_t last = min(i0 + kPruneThreads - 1, n_pairs - 1);
-    if (dst[last] != j) break;
+  const uint64_t total = all ? N : (uint64_t)*prune_n;
+  for (uint64_t it = blockIdx.x; it < total; it += gridDim.x) {
+    const uint32_t j = all ? (uint32_t)it : prune_list[it];
+    const uint32_t extra = min(ovf_cnt[j], (uint32_t)kSlack);
+    if (extra == 0) continue;  // block-uniform
+    const uint32_t* adj = reinterpret_cast<const uint32_t*>(rows + (size_t)j * row_stride);
+    uint32_t mine = kNoNbr;
+    if (tid < kMaxR) mine = adj[tid];
+    const uint32_t d = __syncthreads_count(tid < kMaxR && mine != kNoNbr);
+    if (tid < kMaxR && mine != kNoNbr) sm->c_id[tid] = mine;  // valid entries are the leading ones
+    if (tid < extra) sm->c_id[d + tid] = ovf[(size_t)j * kSlack + tid];
+    __syncthreads();
+    robust_prune<T>(rows, row_stride, vec_units, j, d + extra, alpha, sm->c_id, sm->c_d, sm->s_id, sm->s_d, sm->dead, pv, sm->sel,
+                    sm->scal);
+    __syncthreads();
+    if (tid == 0) { deg[j] = sm->scal[1]; ovf_cnt[j] = 0; }
+    __syncthreads();
   }
-  __syncthreads();
-  const uint32_t total = min(sm->scal[1], deg + cap);
-  if (total == deg) return;
-  if (total <= (uint32_t)kMaxR) {
-    for (uint32_t i = deg + tid; i < total; i += kPruneThreads) adj[i] = sm->c_id[i];
-    return;
-  }
-  robust_prune<T>(rows, row_stride, vec_units, j, total, alpha, sm->c_id, sm->c_d, sm->s_id, sm->s_d, sm->dead, pv, sm->sel,
-                  sm->scal);
 }
 
 // vectors T[N][D] -> HBM rows (adjacency cleared)
@@ -296,9 +292,8 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
   ctas = std::max(1, std::min(ctas, geom.ctas_per_sm));
   const int grid_max = ctas * sms;
   uint8_t* d_q = nullptr; uint64_t* d_ids = nullptr; float* d_dd = nullptr; uint32_t *d_bloom = nullptr, *d_counter = nullptr;
-  uint32_t *d_dump = nullptr, *d_dump_n = nullptr, *d_dst = nullptr, *d_src = nullptr, *d_dst2 = nullptr, *d_src2 = nullptr;
-  uint32_t *d_seg = nullptr, *d_segc = nullptr;
-  void* d_tmp = nullptr; size_t tmp_bytes = 0;
+  uint32_t *d_dump = nullptr, *d_dump_n = nullptr, *d_degc = nullptr, *d_ovf = nullptr, *d_ovfc = nullptr, *d_plist = nullptr,
+           *d_pn = nullptr;
   B_TRY(cudaMalloc(&d_q, (size_t)MB * vec_bytes));
   B_TRY(cudaMalloc(&d_ids, (size_t)MB * 8));
   B_TRY(cudaMalloc(&d_dd, (size_t)MB * 4));
@@ -306,15 +301,16 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
   B_TRY(cudaMalloc(&d_counter, 4));
   B_TRY(cudaMalloc(&d_dump, (size_t)MB * cand_cap * 4));
   B_TRY(cudaMalloc(&d_dump_n, (size_t)MB * 4));
-  const size_t np_max = (size_t)MB * kMaxR;
-  B_TRY(cudaMalloc(&d_dst, np_max * 4)); B_TRY(cudaMalloc(&d_src, np_max * 4));
-  B_TRY(cudaMalloc(&d_dst2, np_max * 4)); B_TRY(cudaMalloc(&d_src2, np_max * 4));
-  B_TRY(cudaMalloc(&d_seg, np_max * 4)); B_TRY(cudaMalloc(&d_segc, 4));
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_dst, d_dst2, d_src, d_src2, (int)np_max);
-  B_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+  B_TRY(cudaMalloc(&d_degc, N * 4));
+  B_TRY(cudaMalloc(&d_ovf, N * (size_t)kSlack * 4));
+  B_TRY(cudaMalloc(&d_ovfc, N * 4));
+  B_TRY(cudaMalloc(&d_plist, N * 4));  // a node enters the list at most once between two of its prunes
+  B_TRY(cudaMalloc(&d_pn, 4));
+  B_TRY(cudaMemset(d_degc, 0, N * 4));
+  B_TRY(cudaMemset(d_ovfc, 0, N * 4));
   const size_t prune_smem = align_up(sizeof(PruneSmem), 16) + (size_t)2 * vec_units * Elem<T>::kPerUnit * 4;
   B_TRY(cudaFuncSetAttribute((const void*)prune_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prune_smem));
-  B_TRY(cudaFuncSetAttribute((const void*)reverse_insert_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prune_smem));
+  B_TRY(cudaFuncSetAttribute((const void*)slack_prune_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prune_smem));
 
   SearchArgs a;
   memset(&a, 0, sizeof(a));
@@ -324,6 +320,10 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
 
   uint64_t done = 0;
   uint32_t bs = 1, n_batches = 0;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) cudaEventCreate(&e);
+  float t_search = 0.f, t_prune = 0.f, t_rev = 0.f;
+  const bool timed = stats_out != nullptr && getenv("BANG_B200_BUILD_TIMERS") != nullptr;
   while (done < n_order) {
     uint32_t B = (uint32_t)std::min<uint64_t>(bs, n_order - done);
     if (done < n_first) B = (uint32_t)std::min<uint64_t>(B, n_first - done);  // a batch never straddles the two passes
@@ -332,27 +332,38 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
     gather_queries_kernel<<<(unsigned)(((size_t)B * vec_bytes + 255) / 256), 256>>>((const uint8_t*)d_vectors, vec_bytes, ids, B, d_q);
     B_TRY(cudaMemsetAsync(d_counter, 0, 4));
     a.Q = B;
+    if (timed) cudaEventRecord(ev[0]);
     kern<<<std::min<int>((B + wpc - 1) / wpc, grid_max), wpc * 32, smem>>>(a);
-    prune_batch_kernel<T><<<B, kPruneThreads, prune_smem>>>(rows, row_stride, vec_units, ids, B, d_dump, d_dump_n, cand_cap, alpha);
+    if (timed) cudaEventRecord(ev[1]);
+    prune_batch_kernel<T><<<B, kPruneThreads, prune_smem>>>(rows, row_stride, vec_units, ids, B, d_dump, d_dump_n, cand_cap, alpha,
+                                                            d_degc, d_ovf, d_ovfc);
+    if (timed) cudaEventRecord(ev[2]);
     const uint32_t np = B * kMaxR;
-    emit_reverse_kernel<<<(np + 255) / 256, 256>>>(rows, row_stride, ids, B, d_dst, d_src);
-    size_t tb = tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_dst, d_dst2, d_src, d_src2, (int)np);
-    B_TRY(cudaMemsetAsync(d_segc, 0, 4));
-    segment_heads_kernel<<<(np + 255) / 256, 256>>>(d_dst2, np, d_seg, d_segc);
-    // one CTA per possible segment; surplus CTAs exit on the device-side count
-    const uint32_t max_segs = std::min<uint64_t>(np, N);
-    reverse_insert_kernel<T><<<max_segs, kPruneThreads, prune_smem>>>(rows, row_stride, vec_units, d_dst2, d_src2, np, d_seg, d_segc, alpha);
+    B_TRY(cudaMemsetAsync(d_pn, 0, 4));
+    reverse_append_kernel<<<(np + 255) / 256, 256>>>(rows, row_stride, ids, B, d_degc, d_ovf, d_ovfc, d_plist, d_pn);
+    slack_prune_kernel<T><<<sms * 8, kPruneThreads, prune_smem>>>(rows, row_stride, vec_units, d_degc, d_ovf, d_ovfc, d_plist, d_pn,
+                                                                  N, false, alpha);
     B_TRY(cudaGetLastError());
+    if (timed) {
+      cudaEventRecord(ev[3]);
+      cudaEventSynchronize(ev[3]);
+      float ms;
+      cudaEventElapsedTime(&ms, ev[0], ev[1]); t_search += ms;
+      cudaEventElapsedTime(&ms, ev[1], ev[2]); t_prune += ms;
+      cudaEventElapsedTime(&ms, ev[2], ev[3]); t_rev += ms;
+    }
     done += B;
     ++n_batches;
     if (bs < MB) bs = std::min<uint32_t>(MB, bs * 2);
   }
+  // final flush: every node with pending reverse edges is pruned over row ∪ side list
+  slack_prune_kernel<T><<<sms * 8, kPruneThreads, prune_smem>>>(rows, row_stride, vec_units, d_degc, d_ovf, d_ovfc, d_plist, d_pn, N,
+                                                                true, alpha_rest);
+  B_TRY(cudaGetLastError());
   B_TRY(cudaDeviceSynchronize());
   // the per-batch scratch is no longer needed: release it before the outputs are materialised
   cudaFree(d_q); cudaFree(d_ids); cudaFree(d_dd); cudaFree(d_bloom); cudaFree(d_counter);
-  cudaFree(d_dump); cudaFree(d_dump_n); cudaFree(d_dst); cudaFree(d_src); cudaFree(d_dst2); cudaFree(d_src2); cudaFree(d_seg);
-  cudaFree(d_segc); cudaFree(d_tmp);
+  cudaFree(d_dump); cudaFree(d_dump_n); cudaFree(d_degc); cudaFree(d_ovf); cudaFree(d_ovfc); cudaFree(d_plist); cudaFree(d_pn);
   if (device_out) {
     // outputs are DEVICE arrays: neighbours ascending, unused slots 0xFFFFFFFF (the search kernel's padding)
     finalize_kernel<<<(unsigned)((N * 32 + 255) / 256), 256>>>(rows, row_stride, N, medoid, h_deg, h_nbrs, kNoNbr);
@@ -368,7 +379,8 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
     B_TRY(cudaMemcpy(h_nbrs, d_nbr, N * kMaxR * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_deg); cudaFree(d_nbr);
   }
-  if (stats_out) stats_out[0] = (float)n_batches;
+  if (stats_out) { stats_out[0] = (float)n_batches; stats_out[1] = t_search; stats_out[2] = t_prune; stats_out[3] = t_rev; }
+  for (auto& e : ev) cudaEventDestroy(e);
   cudaFree(rows);
   return BANG_OK;
 }
