@@ -577,8 +577,9 @@ extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
   CUDA_TRY(cudaMalloc(&c->d_queries, qbytes));
   CUDA_TRY(cudaMalloc(&c->d_ids, (size_t)Q * c->k * sizeof(uint64_t)));
   CUDA_TRY(cudaMalloc(&c->d_dists, (size_t)Q * c->k * sizeof(float)));
-  c->bloom_bytes = (size_t)c->grid * c->warps_per_cta * kBloomWords * 4;
-  CUDA_TRY(cudaMalloc(&c->d_bloom, c->bloom_bytes));
+  // [16-byte block areas of all resident warps (hot, kept in L2)][spill bitmaps (touched only by blocks that overflow)]
+  c->bloom_bytes = (size_t)c->grid * c->warps_per_cta * kVisBlockBytes;
+  CUDA_TRY(cudaMalloc(&c->d_bloom, (size_t)c->grid * c->warps_per_cta * kBloomWords * 4));
   {
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);

@@ -48,15 +48,18 @@ constexpr int kListCap = kMaxR + 8;     // medoid + R neighbours, padded
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
 // The visited filter has the reference's semantics — a 399887-slot bit array addressed by two hashes — but is
 // stored sparsely: 1569 blocks of 255 slots, each block = 16 bytes holding up to 15 one-byte offsets of its set
-// slots (0xFF = empty) plus a count byte.  A search sets a few thousand slots (0.8 % of the array), so 25 KB
+// slots (0xFF = empty) plus a count byte.  A typical search sets a few thousand slots (0.8 % of the array), so 25 KB
 // replace the 50 KB bitmap (and the reference's 400 KB byte array) with identical answers; the filters of all
-// resident queries then fit in L2 next to the PQ codes (ncu: profiles/r1_*).  A block that ever holds more
-// than 15 slots spills into a per-query overflow list.
+// resident queries then fit in L2 next to the PQ codes (ncu: profiles/r1_*).  A block that receives a 16th slot
+// spills into its own 255-bit bitmap (32 bytes, in a separate region that is cleared lazily at the moment of the
+// spill and is otherwise never touched), so the filter stays exact and O(1) for any number of insertions —
+// hard queries on 10^7+ point graphs insert 15-20 thousand slots (profiles/r1_c5.md).
 constexpr uint32_t kVisBlocks = (kBfEntries + 254u) / 255u;        // 1569
-constexpr uint32_t kVisOvfCap = 255u;                               // overflow list entries
-constexpr uint32_t kVisBlockBytes = ((kVisBlocks * 16u + 127u) / 128u) * 128u;   // 25216
-constexpr uint32_t kVisSlotBytes = kVisBlockBytes + 4u * (kVisOvfCap + 1u);       // + counter + list
-constexpr uint32_t kBloomWords = kVisSlotBytes / 4u;  // size of one filter in 32-bit words (host allocation unit)
+constexpr uint32_t kVisBlockBytes = ((kVisBlocks * 16u + 127u) / 128u) * 128u;   // 25216: the 16-byte blocks of one query
+constexpr uint32_t kVisBitmapBytes = ((kVisBlocks * 32u + 127u) / 128u) * 128u;  // 50304: the spill bitmaps of one query
+// One allocation holds [block areas of all resident warps][bitmap areas of all resident warps]; kBloomWords is
+// the per-warp allocation unit in 32-bit words.
+constexpr uint32_t kBloomWords = (kVisBlockBytes + kVisBitmapBytes) / 4u;
 constexpr uint32_t kNoNbr = 0xFFFFFFFFu;  // padding id in the HBM adjacency rows
 constexpr int kAdjBytes = kMaxR * 4;    // 256 B adjacency block at the head of each HBM row
 constexpr int kMaxShards = 8;
@@ -88,7 +91,7 @@ struct SearchArgs {
   const void* queries;      // device T[Q][q_dim]
   uint64_t* out_ids;        // device [Q][k]
   float* out_dists;         // device [Q][k] (query-major)
-  uint32_t* bloom;          // device: one sparse visited filter (kVisSlotBytes) per resident query warp
+  uint32_t* bloom;          // device: one sparse visited filter (kBloomWords words) per resident query warp
   uint32_t* counter;        // device work counter (zeroed before launch)
   uint32_t* st_hops;        // device [Q] or null
   uint32_t* st_sumdeg;
@@ -219,35 +222,39 @@ __device__ __forceinline__ uint4 vis_ld_block(const uint8_t* vis, VisAddr a, uin
   return r;
 }
 // is the slot set, given its block?  Bytes 0..14 hold offsets of set slots or 0xFF; byte 15 counts insertions.
-__device__ __forceinline__ bool vis_test(const uint8_t* vis, uint4 blk, VisAddr a) {
+__device__ __forceinline__ bool vis_test(const uint32_t* vbm, uint4 blk, VisAddr a) {
   const uint32_t pat = (a & 255u) * 0x01010101u;
   // "does any byte equal off": (x - 0x01..) & ~x & 0x80.. is non-zero iff x has a zero byte (exact for the any-test)
   const uint32_t x0 = blk.x ^ pat, x1 = blk.y ^ pat, x2 = blk.z ^ pat, x3 = (blk.w ^ pat) | 0xFF000000u;  // byte 15 = count
   bool found = ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3)) &
                 0x80808080u) != 0;
-  if (!found && (blk.w >> 24) > 15u) {  // the block spilled: scan the overflow list (rare)
-    const uint32_t pos = (a >> 8) * 255u + (a & 255u);
-    const uint32_t* ovf = reinterpret_cast<const uint32_t*>(vis + kVisBlockBytes);
-    const uint32_t m = min(__ldcg(ovf), kVisOvfCap);
-    for (uint32_t i = 0; i < m && !found; ++i) found = __ldcg(ovf + 1 + i) == pos;
+  if (!found && (blk.w >> 24) > 15u) {  // the block spilled: its bitmap holds the 16th and later slots
+    const uint32_t off = a & 255u;
+    found = (__ldcg(vbm + (size_t)(a >> 8) * 8 + (off >> 5)) >> (off & 31u)) & 1u;
   }
   return found;
 }
 // set a slot (not currently set), in two steps so that nothing waits for the atomic's round trip:
 // vis_reserve bumps the block's count byte with one L2 atomic and returns the old count word; vis_commit, called
-// after the distance computations of the hop, stores the offset byte into the reserved position.
+// after the distance computations of the hop, stores the offset byte into the reserved position.  Reservations
+// 15 and up belong to the spill bitmap (vis_spill_*): the one lane that drew number 15 clears the block's bitmap,
+// then, after a warp barrier, every lane with a number >= 15 sets its bit.
 __device__ __forceinline__ uint32_t vis_reserve(uint8_t* vis, VisAddr a) {
   return atomicAdd(reinterpret_cast<uint32_t*>(vis + (size_t)(a >> 8) * 16 + 12), 1u << 24);
 }
-__device__ __forceinline__ void vis_commit(uint8_t* vis, VisAddr a, uint32_t old) {
+__device__ __forceinline__ bool vis_commit(uint8_t* vis, uint32_t* vbm, VisAddr a, uint32_t old) {  // true: spilled
   const uint32_t idx = old >> 24;
-  if (idx < 15u) {
-    vis[(size_t)(a >> 8) * 16 + idx] = (uint8_t)(a & 255u);
-  } else {
-    uint32_t* ovf = reinterpret_cast<uint32_t*>(vis + kVisBlockBytes);
-    const uint32_t j = atomicAdd(ovf, 1u);
-    if (j < kVisOvfCap) ovf[1 + j] = (a >> 8) * 255u + (a & 255u);
+  if (idx < 15u) { vis[(size_t)(a >> 8) * 16 + idx] = (uint8_t)(a & 255u); return false; }
+  if (idx == 15u) {
+    uint4* b = reinterpret_cast<uint4*>(vbm + (size_t)(a >> 8) * 8);
+    b[0] = make_uint4(0u, 0u, 0u, 0u);
+    b[1] = make_uint4(0u, 0u, 0u, 0u);
   }
+  return true;
+}
+__device__ __forceinline__ void vis_spill_set(uint32_t* vbm, VisAddr a) {
+  const uint32_t off = a & 255u;
+  atomicOr(vbm + (size_t)(a >> 8) * 8 + (off >> 5), 1u << (off & 31u));
 }
 
 // Exact squared L2 between one HBM row vector and the query (fp32 copy in shared memory).
@@ -478,13 +485,16 @@ enum { PT_SETUP = 0, PT_ADJWAIT, PT_HASH, PT_BLOOM, PT_COMPACT, PT_CODEWAIT, PT_
 #ifdef BANG_PHASE_TIMERS
 struct Prof {
   long long t, acc[PT_COUNT];
-  __device__ __forceinline__ void start() { for (int i = 0; i < PT_COUNT; ++i) acc[i] = 0; t = clock64(); }
+  __device__ __forceinline__ static long long wall_ns() { long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
+  __device__ __forceinline__ void start() { for (int i = 0; i < PT_COUNT; ++i) acc[i] = 0; acc[PT_TOPK] = wall_ns(); t = clock64(); }
+  __device__ __forceinline__ void stop() { acc[PT_COUNT - 1] = wall_ns() - acc[PT_TOPK]; }  // slot 12: start (ns), slot 15: duration (ns)
   __device__ __forceinline__ void tick(int i) { const long long n = clock64(); acc[i] += n - t; t = n; }
   __device__ __forceinline__ void count(int i) { acc[i] += 1; }
 };
 #else
 struct Prof {
   __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void stop() {}
   __device__ __forceinline__ void tick(int) {}
   __device__ __forceinline__ void count(int) {}
 };
@@ -512,7 +522,7 @@ __device__ __forceinline__ VisPos vis_pos(uint32_t id) {
 // Returns the number of accepted candidates; n_id/n_d hold them unordered; *deg_out = degree of the node.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, int CS>
-__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* vis, uint2 nb2, bool first,
+__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* vis, uint32_t* vbm, uint2 nb2, bool first,
                                            uint32_t* deg_out, Prof& pf) {
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
   const uint32_t id0 = nb2.x, id1 = nb2.y;
@@ -539,8 +549,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
     uint4 b01, b02, b11, b12;
     if (v0) { b01 = vis_ld_block(vis, a01, s.pol_keep); if (MODE != kExact) b02 = vis_ld_block(vis, a02, s.pol_keep); }
     if (v1) { b11 = vis_ld_block(vis, a11, s.pol_keep); if (MODE != kExact) b12 = vis_ld_block(vis, a12, s.pol_keep); }
-    if (v0) { s01 = vis_test(vis, b01, a01); s02 = (MODE == kExact) ? s01 : vis_test(vis, b02, a02); }
-    if (v1) { s11 = vis_test(vis, b11, a11); s12 = (MODE == kExact) ? s11 : vis_test(vis, b12, a12); }
+    if (v0) { s01 = vis_test(vbm, b01, a01); s02 = (MODE == kExact) ? s01 : vis_test(vbm, b02, a02); }
+    if (v1) { s11 = vis_test(vbm, b11, a11); s12 = (MODE == kExact) ? s11 : vis_test(vbm, b12, a12); }
     acc0 = v0 && !(s01 && s02);
     acc1 = v1 && !(s11 && s12);
     ins0 = (s01 ? 0u : 1u) | ((MODE != kExact && !s02) ? 2u : 0u);
@@ -633,13 +643,23 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
     }
   }
   // the reserved filter bytes: the atomics have long returned
-  if (ins0 & 1u) vis_commit(vis, a01, r01);
-  if (ins0 & 2u) vis_commit(vis, a02, r02);
-  if (ins1 & 1u) vis_commit(vis, a11, r11);
-  if (ins1 & 2u) vis_commit(vis, a12, r12);
+  uint32_t spill = 0;
+  if (ins0 & 1u) spill |= vis_commit(vis, vbm, a01, r01) ? 1u : 0u;
+  if (ins0 & 2u) spill |= vis_commit(vis, vbm, a02, r02) ? 2u : 0u;
+  if (ins1 & 1u) spill |= vis_commit(vis, vbm, a11, r11) ? 4u : 0u;
+  if (ins1 & 2u) spill |= vis_commit(vis, vbm, a12, r12) ? 8u : 0u;
   if (first && lane == 0) {
-    vis_commit(vis, am1, rm1);
-    if (MODE != kExact && am2 != am1) vis_commit(vis, am2, rm2);
+    spill |= vis_commit(vis, vbm, am1, rm1) ? 16u : 0u;
+    if (MODE != kExact && am2 != am1) spill |= vis_commit(vis, vbm, am2, rm2) ? 32u : 0u;
+  }
+  if (__any_sync(kFull, spill != 0)) {  // rare: blocks with more than 15 slots
+    __syncwarp();                       // the freshly spilled blocks' bitmaps are cleared
+    if (spill & 1u) vis_spill_set(vbm, a01);
+    if (spill & 2u) vis_spill_set(vbm, a02);
+    if (spill & 4u) vis_spill_set(vbm, a11);
+    if (spill & 8u) vis_spill_set(vbm, a12);
+    if (spill & 16u) vis_spill_set(vbm, am1);
+    if (spill & 32u) vis_spill_set(vbm, am2);
   }
   __syncwarp();
   pf.tick(PT_LUT);
@@ -865,7 +885,10 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
   const uint64_t pol_stream = l2_policy_evict_first();
   s.pol_stream = pol_stream;
   s.pol_keep = l2_policy_evict_last();
-  uint8_t* vis = reinterpret_cast<uint8_t*>(a.bloom) + ((size_t)blockIdx.x * warps + warp) * kVisSlotBytes;
+  // [block areas of all warps of the grid][spill bitmap areas of all warps of the grid]
+  uint8_t* vis = reinterpret_cast<uint8_t*>(a.bloom) + ((size_t)blockIdx.x * warps + warp) * kVisBlockBytes;
+  uint32_t* vbm = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.bloom) + (size_t)gridDim.x * warps * kVisBlockBytes +
+                                              ((size_t)blockIdx.x * warps + warp) * kVisBitmapBytes);
 
   for (;;) {
     uint32_t q = 0;
@@ -882,7 +905,6 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
     {
       uint4* b4 = reinterpret_cast<uint4*>(vis);
       for (uint32_t i = lane; i < kVisBlocks; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
-      if (lane == 0) *reinterpret_cast<uint32_t*>(vis + kVisBlockBytes) = 0;  // overflow counter
     }
     if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
     __syncwarp();
@@ -904,7 +926,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
-      uint32_t n = expand<T, MODE, CS>(a, s, vis, my_nb, true, &deg, pf);
+      uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, true, &deg, pf);
       sum_deg += deg; n_pass += n;
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
@@ -921,7 +943,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
         n = 0;
-        if (have) { n = expand<T, MODE, CS>(a, s, vis, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
+        if (have) { n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
@@ -950,7 +972,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-        const uint32_t n = expand<T, MODE, CS>(a, s, vis, my_nb, first, &deg, pf);
+        const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, &deg, pf);
         sum_deg += deg; n_pass += n;
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
         const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
@@ -999,6 +1021,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       }
     }
 #ifdef BANG_PHASE_TIMERS
+    pf.stop();
     if (lane == 0 && a.st_phase) for (int i = 0; i < PT_COUNT; ++i) a.st_phase[(size_t)q * PT_COUNT + i] = pf.acc[i];
 #endif
     if (lane == 0) {

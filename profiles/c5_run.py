@@ -11,7 +11,7 @@ from bang_b200 import api, build_sharded, recall, sharding
 
 N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 4_000_000
 Q = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
-Ls = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [64, 128, 176, 256]
+Ls = sys.argv[3].split(",") if len(sys.argv) > 3 else ["64", "128", "176", "256"]   # "L" or "L:warps_per_sm"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -27,7 +27,14 @@ if rank == 0:
     print(f"[c5] N={N} built+loaded in {time.time() - t_all:.1f}s {T}; per-GPU HBM {info.device_bytes / 2**30:.1f} GiB; medoid {medoid}", flush=True)
 s.set_dists_layout(api.DISTS_QUERY_MAJOR)
 out = []
-for L in Ls:
+for cfg in Ls:
+    solo = cfg.endswith("s")          # "176s": ranks > 0 stay idle (their shards are still served)
+    L, _, wps = cfg.rstrip("s").partition(":")
+    L = int(L)
+    if wps:
+        os.environ["BANG_B200_WARPS_PER_SM"] = wps
+    else:
+        os.environ.pop("BANG_B200_WARPS_PER_SM", None)
     s.bang_set_searchparams(10, L)
     s.bang_alloc(Q)
     ms, e2e = [], []
@@ -35,10 +42,34 @@ for L in Ls:
         s.bang_init(Q)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
+        if solo and rank != 0 and r > 0:
+            ms.append(0.0); e2e.append(0.0)
+            dist.barrier()
+            continue
         ids, d = s.bang_query(my_q)
+        if solo:
+            dist.barrier()
         e2e.append((time.perf_counter() - t0) * 1e3)
         ms.append(s.last_timing().kernel_ms)
     st = s.last_stats(Q)
+    if os.environ.get("C5_PHASES") and rank == 0:
+        import ctypes
+        fn = s._lib.bang_b200_debug_phase_clocks
+        fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        ph = np.zeros((Q, 16), dtype=np.int64)
+        if fn(s._h, ph.ctypes.data) == 0:
+            names = ["setup", "adjwait", "hash", "bloom", "compact", "codewait", "lut", "scan", "decide", "merge", "unvis", "rerank"]
+            hops = ph[:, 13].mean()
+            cyc = ph[:, :12].sum(1); ns = ph[:, 15]; t0 = ph[:, 12] - ph[:, 12].min()
+            print(f"[c5] per-query cycles mean {cyc.mean():.0f} p99 {np.percentile(cyc, 99):.0f} max {cyc.max()}; wall us mean {ns.mean() / 1e3:.0f} p99 "
+                  f"{np.percentile(ns, 99) / 1e3:.0f} max {ns.max() / 1e3:.0f}; SM clock GHz {cyc.sum() / ns.sum():.3f}; last start {t0.max() / 1e6:.2f} ms, "
+                  f"last end {(t0 + ns).max() / 1e6:.2f} ms", flush=True)
+            for qi in np.argsort(-ns)[:4]:
+                print(f"[c5] slow query {qi}: wall {ns[qi] / 1e3:.0f} us start {t0[qi] / 1e6:.2f} ms hops {ph[qi, 13]} merges {ph[qi, 14]} n_cand {st['n_cand'][qi]} sum_deg {st['sum_deg'][qi]} kcycles",
+                      {n: int(ph[qi, i] // 1000) for i, n in enumerate(names)}, flush=True)
+            print("[c5] phase clocks per hop:", {n: int(ph[:, i].mean() / (hops if n not in ("setup", "rerank") else 1)) for i, n in enumerate(names)}, flush=True)
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, round(float(np.mean(ms[2:])), 2))
     k_ms = sharding.max_over_ranks([float(np.mean(ms[2:]))], device=torch.device("cuda", local))[0]
     e_ms = sharding.max_over_ranks([float(np.mean(e2e[2:]))], device=torch.device("cuda", local))[0]
     esz = 1
@@ -48,7 +79,7 @@ for L in Ls:
     if rank == 0:
         rec = recall.calculate_recall(gt_ids[:n_gt], gt_d[:n_gt], ids[:n_gt], 10)
         line = {"metric": "QPS at recall@10 (batched greedy Vamana search, SIFT1B-shape, graph sharded over HBM)", "n_gpus": world,
-                "N": N, "L": L, "recall_at_10": round(rec, 2), "recall_queries": n_gt, "kernel_ms_max_over_ranks": k_ms,
+                "N": N, "L": L, "warps_per_sm": int(wps) if wps else 16, "solo": solo, "kernel_ms_per_rank": per_rank, "recall_at_10": round(rec, 2), "recall_queries": n_gt, "kernel_ms_max_over_ranks": k_ms,
                 "value": world * Q / (k_ms * 1e-3), "e2e": world * Q / (e_ms * 1e-3), "unit": "QPS",
                 "queries_per_gpu": Q, "hops_per_query": float(st["hops"].mean()), "candidates_per_query": float(st["n_cand"].mean()),
                 "bytes_per_query": float(bq.mean()), "nvlink_bytes_per_query": float(nvlink.mean()),

@@ -262,3 +262,46 @@ def test_reference_driver_runs_on_this_library(fx_u8):
     for L in (10, 34, 106):
         ids, _, _, _ = _search(fx, "base", 10, L)
         assert abs(got[L] - recall.calculate_recall(fx.gt_ids, fx.gt_dists, ids, 10)) < 0.01
+
+
+@pytest.mark.parametrize("mode,L", [("inmemory", 512), ("base", 300), ("exact", 128)])
+def test_visited_filter_spill_blocks(tmp_path, mode, L):
+    """A random 64-regular graph hands every hop ~64 unseen ids: 2 x 64 x (L + 120) slots of the 399 887-slot filter
+    get set (tens per 255-slot block), so most blocks of the sparse filter spill into their bitmaps.  The answers
+    must still be those of the reference's plain array (hashFn1_d/hashFn2_d + neighbor_filtering_new,
+    bang_search.cu:1140-1189), i.e. the oracle's."""
+    import torch
+    from bang_b200 import synth
+    rng = np.random.default_rng(77)
+    N, D, R, m = 60_000, 32, 64, 8
+    base = rng.integers(0, 256, size=(N, D), dtype=np.uint8)
+    r = rng.integers(0, N - 1, size=(N, R))
+    while True:   # rows of distinct neighbours, no self loops (as any Vamana index has)
+        srt = np.sort(r, axis=1)
+        dup = np.nonzero((srt[:, 1:] == srt[:, :-1]).any(1))[0]
+        if len(dup) == 0:
+            break
+        r[dup] = rng.integers(0, N - 1, size=(len(dup), R))
+    nbrs = ((np.arange(N)[:, None] + 1 + r) % N).astype(np.uint32)
+    deg = np.full(N, R, dtype=np.uint32)
+    piv, cen, offs = synth.train_pq(torch.from_numpy(base), m, iters=4)
+    codes = synth.encode_pq(torch.from_numpy(base), piv, cen, offs).numpy()
+    prefix = str(tmp_path / "rnd")
+    formats.write_index(prefix, base, deg, nbrs, 123, piv, cen, offs, codes)
+    queries = rng.integers(0, 256, size=(24, D), dtype=np.uint8)
+    s = api.BANGSearch("uint8", mode)
+    assert s.bang_load(prefix)
+    s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+    s.bang_set_searchparams(10, L)
+    s.bang_alloc(len(queries))
+    s.bang_init(len(queries))
+    ids, dists = s.bang_query(queries)
+    stats = s.last_stats(len(queries))
+    s.bang_free()
+    s.bang_unload()
+    ox = O.OracleIndex(formats.pack_disk_bin(base, deg, nbrs), "uint8", D, R, 123, codes, piv, cen, offs)
+    oids, od, ost = ox.search(queries, 10, L, mode=MODE_O[mode], order=O.ORDER_GPU, stats=True)
+    assert stats["n_cand"].mean() > 15_000 or mode == "exact"   # the case really is a heavy one
+    assert np.array_equal(ids, oids), f"{(ids != oids).any(1).sum()} of {len(ids)} queries differ"
+    assert np.array_equal(dists.view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(stats["n_cand"], ost["n_cand"]) and np.array_equal(stats["hops"], ost["hops"])
