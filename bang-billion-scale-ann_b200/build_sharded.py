@@ -245,6 +245,8 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
 
     # ---- hand the rows and the codes to the search library ----
     t0 = time.time()
+    del deg
+    torch.cuda.empty_cache()   # the library allocates with cudaMalloc: hand torch's cached blocks back first (1e9 points: 80 GB needed)
     search.load_device_begin(N, D, medoid, piv.cpu().numpy(), cen.cpu().numpy(), offs)
     step = 1 << 22
     for a in range(0, n_own, step):
@@ -253,13 +255,19 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
     del own_vec, adj_own
     torch.cuda.empty_cache()
     piv_np, cen_np = piv.cpu().numpy(), cen.cpu().numpy()
-    for c in range(n_chunks):
-        n = min(chunk, N - c * chunk)
-        codes = torch.empty((n, m), dtype=torch.uint8, device=dev)
-        if c % G == rank:
-            codes.copy_(synth.encode_pq(gen_chunk(centers, c, n, seed), piv_np, cen_np, offs))
-        dist.broadcast(codes, c % G)
-        search.load_device_codes(c * chunk, n, codes.data_ptr())
+    for c0 in range(0, n_chunks, G):   # G chunks at a time: every rank encodes one of them, then G broadcasts
+        mine = None
+        c_me = c0 + rank
+        if c_me < n_chunks:
+            n_me = min(chunk, N - c_me * chunk)
+            mine = synth.encode_pq(gen_chunk(centers, c_me, n_me, seed), piv_np, cen_np, offs)
+        for c in range(c0, min(n_chunks, c0 + G)):
+            n = min(chunk, N - c * chunk)
+            codes = mine if c == c_me else torch.empty((n, m), dtype=torch.uint8, device=dev)
+            dist.broadcast(codes, c % G)
+            search.load_device_codes(c * chunk, n, codes.data_ptr())
+        torch.cuda.synchronize()
+        del mine, codes
     search.load_device_end()
     T["load"] = time.time() - t0
     my_q = queries[rank * n_queries_per_rank:(rank + 1) * n_queries_per_rank].cpu().numpy()

@@ -98,6 +98,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(workload: str, mode: str, L: int, q: int):
+    """DRAM bytes (read + write) of one launch of the search kernel from the committed ncu capture, if that
+    capture was taken on this very workload / mode / L / batch; else None (B200 bench contract: traffic or null)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as f:
+            t = json.load(f)
+        if (t["workload"], t["mode"], t["L"], t["queries"]) == (workload, mode, L, q):
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------------------------
 # index generation
 # ----------------------------------------------------------------------------------------------------
@@ -370,7 +383,8 @@ def run_b200(args):
                          "e2e": p95["e2e_qps"], "bytes_per_query": p95["bytes_per_query"]},
         "gpu_launches": args.steps * 1,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                     "traffic": None, "kernel": "bang_search_kernel (fused traversal, 1 launch per step)",
+                     "traffic": ncu_traffic(args.workload, wl["mode"], p90["L"], wl["q"]),
+                     "kernel": "bang_search_kernel (fused traversal, 1 launch per step)",
                      "bytes_per_query": p90["bytes_per_query"], "hops_per_query": p90["hops"],
                      "candidates_per_query": p90["n_cand"], "peak_source": peak_src,
                      "grid": tm.grid, "block": tm.block, "smem_bytes": tm.smem_bytes, "ctas_per_sm": tm.ctas_per_sm},

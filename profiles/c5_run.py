@@ -27,6 +27,15 @@ if rank == 0:
     print(f"[c5] N={N} built+loaded in {time.time() - t_all:.1f}s {T}; per-GPU HBM {info.device_bytes / 2**30:.1f} GiB; medoid {medoid}", flush=True)
 s.set_dists_layout(api.DISTS_QUERY_MAJOR)
 out = []
+try:   # SM clock + throttle reasons sampled right after each timed batch (same process, NVML)
+    import pynvml
+    pynvml.nvmlInit()
+    _nv = pynvml.nvmlDeviceGetHandleByIndex(local)
+    def sample_clock():
+        return (pynvml.nvmlDeviceGetClockInfo(_nv, pynvml.NVML_CLOCK_SM), int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(_nv)))
+except Exception:
+    def sample_clock():
+        return (0, 0)
 for cfg in Ls:
     solo = cfg.endswith("s")          # "176s": ranks > 0 stay idle (their shards are still served)
     L, _, wps = cfg.rstrip("s").partition(":")
@@ -37,8 +46,8 @@ for cfg in Ls:
         os.environ.pop("BANG_B200_WARPS_PER_SM", None)
     s.bang_set_searchparams(10, L)
     s.bang_alloc(Q)
-    ms, e2e = [], []
-    for r in range(5):
+    ms, e2e, clk = [], [], []
+    for r in range(7):
         s.bang_init(Q)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -50,6 +59,7 @@ for cfg in Ls:
         if solo:
             dist.barrier()
         e2e.append((time.perf_counter() - t0) * 1e3)
+        clk.append(sample_clock())
         ms.append(s.last_timing().kernel_ms)
     st = s.last_stats(Q)
     if os.environ.get("C5_PHASES") and rank == 0:
@@ -70,6 +80,8 @@ for cfg in Ls:
             print("[c5] phase clocks per hop:", {n: int(ph[:, i].mean() / (hops if n not in ("setup", "rerank") else 1)) for i, n in enumerate(names)}, flush=True)
     per_rank = [None] * world
     dist.all_gather_object(per_rank, round(float(np.mean(ms[2:])), 2))
+    clk_rank = [None] * world
+    dist.all_gather_object(clk_rank, [int(np.median([c[0] for c in clk] or [0])), int(np.bitwise_or.reduce([c[1] for c in clk] or [0]))])
     k_ms = sharding.max_over_ranks([float(np.mean(ms[2:]))], device=torch.device("cuda", local))[0]
     e_ms = sharding.max_over_ranks([float(np.mean(e2e[2:]))], device=torch.device("cuda", local))[0]
     esz = 1
@@ -79,20 +91,19 @@ for cfg in Ls:
     if rank == 0:
         rec = recall.calculate_recall(gt_ids[:n_gt], gt_d[:n_gt], ids[:n_gt], 10)
         line = {"metric": "QPS at recall@10 (batched greedy Vamana search, SIFT1B-shape, graph sharded over HBM)", "n_gpus": world,
-                "N": N, "L": L, "warps_per_sm": int(wps) if wps else 16, "solo": solo, "kernel_ms_per_rank": per_rank, "recall_at_10": round(rec, 2), "recall_queries": n_gt, "kernel_ms_max_over_ranks": k_ms,
+                "N": N, "L": L, "warps_per_sm": int(wps) if wps else 16, "solo": solo, "kernel_ms_per_rank": per_rank, "sm_mhz_and_event_reasons_per_rank": clk_rank, "kernel_ms_runs_rank0": [round(x, 2) for x in ms], "recall_at_10": round(rec, 2), "recall_queries": n_gt, "kernel_ms_max_over_ranks": k_ms,
                 "value": world * Q / (k_ms * 1e-3), "e2e": world * Q / (e_ms * 1e-3), "unit": "QPS",
                 "queries_per_gpu": Q, "hops_per_query": float(st["hops"].mean()), "candidates_per_query": float(st["n_cand"].mean()),
                 "bytes_per_query": float(bq.mean()), "nvlink_bytes_per_query": float(nvlink.mean()),
                 "per_gpu_hbm_gib": info.device_bytes / 2**30, "build_seconds": T}
         print(json.dumps(line), flush=True)
         out.append(line)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"c5_{N}.jsonl"), "w") as f:   # rewritten after every L: a cut-off run keeps what it measured
+            for l in out:
+                f.write(json.dumps(l) + "\n")
     s.bang_free()
 dist.barrier()
-if rank == 0:
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"c5_{N}.jsonl"), "w") as f:
-        for l in out:
-            f.write(json.dumps(l) + "\n")
 s.bang_unload()
 dist.barrier()
 dist.destroy_process_group()
