@@ -1,12 +1,13 @@
-// search_kernel.cuh — the fused, persistent, per-query-block traversal kernel for sm_100a.
+// search_kernel.cuh — the fused, persistent traversal kernel for sm_100a.
 //
 // One warp owns one query at a time and walks the whole greedy search for it without leaving the SM:
-// PQ table build (stage 1) -> { adjacency fetch, visited filter (stage 4a), PQ/exact distances
-// (stage 3), parent selection (stage 2), (dist,id) sort + worklist merge (stage 4b) }* -> exact re-rank
-// + top-k (stage 5).  CTAs (= one warp) are persistent: the grid is sized to the number of resident CTAs
-// and each pulls query indices from a global counter.  What the reference does with ~5 kernel launches,
-// 2 memsets, up to 5 PCIe copies and 3 stream syncs per hop (bang_search.cu:701-958) is one launch here;
-// the LUT, worklist, candidate log and neighbour lists never leave shared memory.
+// { adjacency fetch, visited filter (stage 4a), PQ/exact distances (stages 1+3, the table entries are
+// evaluated on demand), parent selection (stage 2), (dist,id) sort + worklist merge (stage 4b) }* -> exact
+// re-rank + top-k (stage 5).  CTAs (up to 16 query warps + one pivot table) are persistent: the grid is sized
+// to the number of resident CTAs and every warp pulls query indices from a global counter.  What the reference
+// does with ~5 kernel launches, 2 memsets, up to 5 PCIe copies and 3 stream syncs per hop
+// (bang_search.cu:701-958) is one launch here; the worklist, candidate log and neighbour lists never leave
+// shared memory.
 //
 // Why one warp per query and no per-query LUT: the search is a dependent pointer chase whose per-hop
 // work is tiny (64 hashes, ~10 PQ distances, a 150-entry merge), so throughput = resident queries /
@@ -19,8 +20,9 @@
 // publish the pivot table); afterwards every warp runs on its own with __syncwarp and redux.sync.
 // Per hop:
 //   * the adjacency row (256 B) was requested at the end of the previous hop, one 8-byte load per lane;
-//   * visited filter with snapshot semantics: 4 bloom words per lane in one L2 round trip, insertion
-//     by fire-and-forget `red.or` (nothing waits on it);
+//   * visited filter with snapshot semantics: 4 filter blocks (16 B each) per lane in one L2 round trip;
+//     insertion = one atomic on the block's count (hands out the byte position) + a byte store after the
+//     distance phase, so nothing waits on the atomic's round trip;
 //   * 8 lanes per accepted candidate for the distance, 16 candidates' code loads in flight;
 //   * the next node to expand is decided from the unsorted distances BEFORE the sort/merge (it is the
 //     smaller of the best admitted new candidate and the first unvisited worklist entry — exactly what
@@ -171,9 +173,9 @@ __device__ __forceinline__ const uint8_t* row_ptr(const SearchArgs& a, uint32_t 
   return a.rows[s] + (size_t)(id / a.n_shards) * a.row_stride;  // local HBM or a peer mapping over NVLink
 }
 
-// L2 residency control.  The per-query bloom filters (50 KB each, re-read every hop) are the only data
-// with reuse; graph rows and PQ codes are touched once per query.  Streaming loads therefore carry an
-// evict-first L2 policy and bypass L1, bloom accesses an evict-last policy, so the gathers do not push the
+// L2 residency control.  The per-query visited filters (25 KB of blocks each, re-read every hop) are the only
+// data with reuse; graph rows and PQ codes are touched once per query.  Streaming loads therefore carry an
+// evict-first L2 policy and bypass L1, filter accesses an evict-last policy, so the gathers do not push the
 // filters out of the 126 MB L2 (ncu: profiles/r1_*: DRAM bytes vs algorithmic bytes).
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;

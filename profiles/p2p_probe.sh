@@ -1,0 +1,15 @@
+#!/bin/bash
+# Next-round first step (needs 2 GPUs): gpurun --gpus 2 --timeout 600 -- 'bash profiles/p2p_probe.sh > gpurun_out/p2p_probe.jsonl 2> gpurun_out/p2p_probe.err'
+# Footprints = the per-GPU row buffers of the measured C5 runs (MiB): 4M/2 732, 9M/2 1648 (slow), 64M/8 2930 (slow),
+# 32M/2 5860 (fast), 256M/4 23438 (slow), plus 64 (L2-resident) and 46000 (1e9 points / 8 GPUs).
+set -e
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o /tmp/p2p_probe profiles/p2p_probe.cu -lcuda
+S=64,732,1648,2930,5860,23438,46000
+for mode in local peer vmm; do /tmp/p2p_probe $mode $S; done
+for mib in 64 732 1648 2930 5860 23438 46000; do
+  /tmp/p2p_probe ipc $mib
+  /tmp/p2p_probe ipc $mib 16 2000 4 1     # owner heap fragmented first
+done
+/tmp/p2p_probe peer $S 16 2000 4 1
+/tmp/p2p_probe peer 1648,5860 4           # concurrency dependence
+/tmp/p2p_probe ipc 1648 4
