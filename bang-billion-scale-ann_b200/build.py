@@ -23,6 +23,8 @@ ORACLE = os.path.join(ROOT, "oracle")
 LIB_CUDA = os.path.join(PKG_DIR, "libbang_b200.so")
 LIB_FIXTURE = os.path.join(PKG_DIR, "libbang_fixture.so")
 CLI = os.path.join(PKG_DIR, "bang_search")
+LIB_PREPROCESS = os.path.join(PKG_DIR, "libbang_preprocess.so")
+CLI_PREPROCESS = os.path.join(PKG_DIR, "bang_preprocess")
 LIB_ORACLE = os.path.join(ORACLE, "libbang_oracle.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -82,6 +84,17 @@ def build_cli(force: bool = False) -> str:
     return CLI
 
 
+def build_preprocess(force: bool = False) -> str:
+    """DiskANN .index -> BANG .bin converter (host only): shared library for ctypes + the CLI with the reference
+    script's argument list (BANG_Base/bang_preprocess.py)."""
+    src = os.path.join(CSRC, "bang_preprocess.cpp")
+    if not force and _newer(LIB_PREPROCESS, [src]) and _newer(CLI_PREPROCESS, [src]):
+        return LIB_PREPROCESS
+    _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", LIB_PREPROCESS])
+    _run(["g++", "-O2", "-std=c++17", "-DBANG_PREPROCESS_MAIN", src, "-o", CLI_PREPROCESS])
+    return LIB_PREPROCESS
+
+
 def build_fixture(force: bool = False) -> str:
     src = os.path.join(CSRC, "fixture_builder.cpp")
     if not force and _newer(LIB_FIXTURE, [src]):
@@ -117,6 +130,7 @@ def build_reference(force: bool = False) -> str | None:
 
 def build_all(force: bool = False) -> None:
     build_fixture(force)
+    build_preprocess(force)
     build_oracle(force)
     build_cuda(force)
     build_cli(force)

@@ -247,3 +247,57 @@ def write_index(prefix: str, vectors, degrees, nbrs, medoid: int, pivots=None, c
         write_pq_pivots_old(p.old_pivots, pivots, centroid, chunk_offsets)
         write_bin(p.pq_compressed, np.asarray(codes, dtype=np.uint8))
     return p
+
+
+# ----------------------------------------------------------------------------------------------------
+# DiskANN `_disk.index` (what `build_disk_index` writes) and its conversion to `_disk.bin` + `_disk_metadata.bin`
+# (BANG_Base/bang_preprocess.py; C++ here: csrc/bang_preprocess.cpp)
+# ----------------------------------------------------------------------------------------------------
+def write_diskann_index(path: str, vectors: np.ndarray, degrees: np.ndarray, nbrs: np.ndarray, medoid: int,
+                        sector_len: int = 4096, rng: np.random.Generator | None = None) -> None:
+    """Writes the on-disk layout the reference's converter reads (bang_preprocess.py:26-63,70-102): a metadata sector
+    (two int32, then uint64 npts, ndims, medoid, max_node_len, nnodes_per_sector, 3 unused, file size) followed by
+    sectors of nnodes_per_sector entries `T[D] | u32 degree | u32 nbr[R]` packed from the start of each sector.
+    Neighbour slots beyond the degree hold arbitrary bytes in a real index: `rng` fills them with noise."""
+    n, d = vectors.shape
+    R = nbrs.shape[1]
+    node_len = d * vectors.dtype.itemsize + 4 + 4 * R
+    per_sector = sector_len // node_len
+    if per_sector < 1:
+        raise ValueError("node entry larger than a sector")
+    n_sectors = 1 + (n + per_sector - 1) // per_sector
+    nb = np.array(nbrs, dtype="<u4", copy=True)
+    if rng is not None:
+        noise = rng.integers(0, 2**32, size=nb.shape, dtype=np.uint64).astype("<u4")
+        unused = np.arange(R)[None, :] >= np.asarray(degrees)[:, None]
+        nb[unused] = noise[unused]
+    entries = np.zeros((n, node_len), dtype=np.uint8)
+    vb = d * vectors.dtype.itemsize
+    entries[:, :vb] = np.ascontiguousarray(vectors).view(np.uint8).reshape(n, vb)
+    entries[:, vb:vb + 4] = np.asarray(degrees, dtype="<u4").reshape(n, 1).view(np.uint8)
+    entries[:, vb + 4:] = nb.view(np.uint8).reshape(n, 4 * R)
+    buf = np.zeros(n_sectors * sector_len, dtype=np.uint8)
+    hdr = struct.pack("<ii9Q", 9, 1, n, d, medoid, node_len, per_sector, 0, 0, 0, n_sectors * sector_len)
+    buf[:len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
+    for s in range(1, n_sectors):
+        lo = (s - 1) * per_sector
+        blk = entries[lo:lo + per_sector].reshape(-1)
+        buf[s * sector_len:s * sector_len + blk.size] = blk
+    buf.tofile(path)
+
+
+def convert_diskann_index(index_path: str, out_bin_path: str, dim: int, dtype: str, degree: int, sector_len: int = 4096) -> int:
+    """`bang_preprocess.py <index> <out.bin> <dim> <datatype> <R>` through csrc/bang_preprocess.cpp; returns the
+    number of nodes written.  Creates out_bin_path and <out>_metadata.bin."""
+    import ctypes
+    from . import build
+    lib = ctypes.CDLL(build.build_preprocess())
+    lib.bang_preprocess_index.restype = ctypes.c_int
+    lib.bang_preprocess_index.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                          ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64)]
+    lib.bang_preprocess_last_error.restype = ctypes.c_char_p
+    n = ctypes.c_uint64(0)
+    rc = lib.bang_preprocess_index(index_path.encode(), out_bin_path.encode(), dim, DTYPE_CODE[dtype], degree, sector_len, ctypes.byref(n))
+    if rc != 0:
+        raise ValueError(lib.bang_preprocess_last_error().decode())
+    return int(n.value)

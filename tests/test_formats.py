@@ -84,3 +84,29 @@ def test_truthset_roundtrip(tmp_path, fx_u8):
         f.write(b"12345678")
     with pytest.raises(ValueError):
         formats.read_truthset(p)
+
+
+def test_cli_mips_query_normaliser(tmp_path):
+    """`bang_search <query.bin> <n>` = the reference driver's 2-argument form (test_driver.cpp:280-336,566-571):
+    every float query is scaled to unit norm, one zero dimension is appended, result in <file>_transformed."""
+    import subprocess
+    from bang_b200 import build
+    exe = build.build_cli()
+    rng = np.random.default_rng(3)
+    q = rng.normal(size=(17, 24)).astype(np.float32)
+    path = str(tmp_path / "q.bin")
+    formats.write_bin(path, q)
+    out = subprocess.run([exe, path, "11"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = formats.read_bin(path + "_transformed", np.float32)
+    assert got.shape == (11, 25)
+    want = np.zeros((11, 25), np.float32)
+    for i in range(11):
+        norm = np.float32(0)
+        for j in range(24):
+            norm = np.float32(norm + q[i, j] * q[i, j])     # float accumulation in element order
+        want[i, :24] = q[i] / np.sqrt(norm)
+    assert np.array_equal(got[:, 24], np.zeros(11, np.float32))
+    assert np.allclose(got, want, rtol=2e-7, atol=0)          # (fma contraction may differ by an ulp)
+    # too many queries requested: error, no crash
+    assert subprocess.run([exe, path, "18"], capture_output=True, text=True, timeout=120).returncode != 0

@@ -51,7 +51,7 @@ def _worker(rank, world, port, out):
 
 def test_two_ranks_gloo():
     world = 2
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     for rank in range(world):
