@@ -23,6 +23,7 @@ ORACLE = os.path.join(ROOT, "oracle")
 LIB_CUDA = os.path.join(PKG_DIR, "libbang_b200.so")
 LIB_FIXTURE = os.path.join(PKG_DIR, "libbang_fixture.so")
 CLI = os.path.join(PKG_DIR, "bang_search")
+CLI_INMEM = os.path.join(PKG_DIR, "bang")
 LIB_PREPROCESS = os.path.join(PKG_DIR, "libbang_preprocess.so")
 CLI_PREPROCESS = os.path.join(PKG_DIR, "bang_preprocess")
 LIB_ORACLE = os.path.join(ORACLE, "libbang_oracle.so")
@@ -84,6 +85,16 @@ def build_cli(force: bool = False) -> str:
     return CLI
 
 
+def build_cli_inmem(force: bool = False) -> str:
+    """`bang`: the 15-argument command line of the reference's Inmemory / Exactdistance forks (parANN.cu:79-93)."""
+    src = os.path.join(CSRC, "bang_inmem_main.cpp")
+    if not force and _newer(CLI_INMEM, [src, LIB_CUDA] + _srcs(INCLUDE)):
+        return CLI_INMEM
+    _run(["g++", "-O2", "-std=c++17", "-I", INCLUDE, src, "-o", CLI_INMEM,
+          "-L", PKG_DIR, "-lbang_b200", f"-Wl,-rpath,{PKG_DIR}", "-Wl,-rpath,$ORIGIN"])
+    return CLI_INMEM
+
+
 def build_preprocess(force: bool = False) -> str:
     """DiskANN .index -> BANG .bin converter (host only): shared library for ctypes + the CLI with the reference
     script's argument list (BANG_Base/bang_preprocess.py)."""
@@ -134,6 +145,7 @@ def build_all(force: bool = False) -> None:
     build_oracle(force)
     build_cuda(force)
     build_cli(force)
+    build_cli_inmem(force)
     build_reference(force)
 
 

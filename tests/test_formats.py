@@ -110,3 +110,27 @@ def test_cli_mips_query_normaliser(tmp_path):
     assert np.allclose(got, want, rtol=2e-7, atol=0)          # (fma contraction may differ by an ulp)
     # too many queries requested: error, no crash
     assert subprocess.run([exe, path, "18"], capture_output=True, text=True, timeout=120).returncode != 0
+
+
+def test_inmemory_cli_argument_set(tmp_path):
+    """`bang` takes the 15 positional arguments of the Inmemory / Exactdistance forks (parANN.cu:79-93); without a GPU
+    it gets as far as creating the handle and reports the CUDA error (no CPU fallback)."""
+    import subprocess
+    from bang_b200 import build
+    from conftest import has_gpu
+    exe = build.build_cli_inmem()
+    assert subprocess.run([exe], capture_output=True, text=True).returncode == 1
+    args = ["p.bin", "c.bin", "g.bin", "q.bin", "o.bin", "cen.bin", "gt.bin", "10", "1", "256", "512", "256", "10", "64", "0"]
+    r = subprocess.run([exe] + args, capture_output=True, text=True, env={k: v for k, v in os.environ.items() if k != "BANG_B200_MEDOID"})
+    assert r.returncode == 1 and "medoid" in r.stdout
+    r = subprocess.run([exe] + args + ["5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Could not open the file4" in r.stdout
+    q = np.zeros((12, 8), np.uint8)
+    formats.write_bin(str(tmp_path / "q.bin"), q)
+    formats.write_bin(str(tmp_path / "c.bin"), np.zeros((100, 4), np.uint8))
+    a2 = [str(tmp_path / "p.bin"), str(tmp_path / "c.bin"), str(tmp_path / "g.bin"), str(tmp_path / "q.bin")] + args[4:]
+    r = subprocess.run([exe] + a2[:7] + ["13"] + a2[8:] + ["5"], capture_output=True, text=True)
+    assert r.returncode == 1 and "out of range" in r.stdout          # more queries than the file holds
+    if not has_gpu():
+        r = subprocess.run([exe] + a2 + ["5", "20"], capture_output=True, text=True)
+        assert r.returncode == 2 and ("no CUDA device" in r.stdout or "cudaGetDeviceCount" in r.stdout)

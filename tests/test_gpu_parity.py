@@ -305,3 +305,24 @@ def test_visited_filter_spill_blocks(tmp_path, mode, L):
     assert np.array_equal(ids, oids), f"{(ids != oids).any(1).sum()} of {len(ids)} queries differ"
     assert np.array_equal(dists.view(np.uint32), od.view(np.uint32))
     assert np.array_equal(stats["n_cand"], ost["n_cand"]) and np.array_equal(stats["hops"], ost["hops"])
+
+
+def test_inmemory_cli_reports_recall(fx_u8):
+    """`bang` with the Inmemory fork's 15-argument command line (parANN.cu:79-93) + medoid and L: same recall as the API."""
+    fx = fx_u8
+    exe = build.build_cli_inmem()
+    p = fx.paths
+    L, k = 48, 10
+    ids, _, _, _ = _search(fx, "inmemory", k, L)
+    want = recall.calculate_recall(fx.gt_ids, fx.gt_dists, ids, k)
+    env = dict(os.environ, BANG_B200_DTYPE="uint8")
+    env.pop("BANG_B200_MODE", None)
+    out = subprocess.run([exe, p.old_pivots, p.pq_compressed, p.disk, p.query, p.old_chunk_offsets, p.old_centroid, p.truth,
+                          str(len(fx.queries)), "1", "256", "512", "256", str(k), "64", "0", str(fx.medoid), str(L)],
+                         capture_output=True, text=True, env=env, stdin=subprocess.DEVNULL, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.splitlines()
+    assert lines[0] == f"{fx.medoid}\t{len(fx.queries)}"
+    assert any(ln.startswith("Throughput = ") for ln in lines) and "Try Next run ? [y|n]" in lines
+    row = lines[lines.index(f"Ls\tRecall@{k}") + 1].split("\t")
+    assert int(row[0]) == L and abs(float(row[1]) - want) < 0.006
