@@ -30,7 +30,8 @@ NO_ID = 0xFFFFFFFF
 # every symbol include/bang_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "bang_b200_create", "bang_b200_destroy", "bang_b200_load", "bang_b200_load_files", "bang_b200_set_sharding",
-    "bang_b200_export_shard", "bang_b200_import_shard", "bang_b200_load_device_begin", "bang_b200_load_device_rows",
+    "bang_b200_export_shard", "bang_b200_import_shard", "bang_b200_export_shard_fd", "bang_b200_import_shard_fd",
+    "bang_b200_load_device_begin", "bang_b200_load_device_rows",
     "bang_b200_load_device_codes", "bang_b200_load_device_end", "bang_b200_set_searchparams", "bang_b200_alloc",
     "bang_b200_init", "bang_b200_query", "bang_b200_free", "bang_b200_unload", "bang_b200_set_dists_layout",
     "bang_b200_query_device", "bang_b200_pq_table", "bang_b200_info", "bang_b200_last_stats",
@@ -79,6 +80,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         "bang_b200_set_sharding": (ci, [vp, ci, ci]),
         "bang_b200_export_shard": (ci, [vp, vp]),
         "bang_b200_import_shard": (ci, [vp, ci, vp]),
+        "bang_b200_export_shard_fd": (ci, [vp, ctypes.POINTER(ci), ctypes.POINTER(u64)]),
+        "bang_b200_import_shard_fd": (ci, [vp, ci, ci, u64]),
         "bang_b200_load_device_begin": (ci, [vp, u64, u32, u64, u32, vp, vp, vp]),
         "bang_b200_load_device_rows": (ci, [vp, u64, u64, vp, vp]),
         "bang_b200_load_device_codes": (ci, [vp, u64, u64, vp]),
@@ -203,6 +206,16 @@ class BANGSearch:
     def import_shard(self, shard: int, handle: bytes) -> None:
         buf = ctypes.create_string_buffer(handle, 64)
         self._check(self._lib.bang_b200_import_shard(self._h, shard, buf))
+
+    def export_shard_fd(self) -> tuple[int, int]:
+        """(file descriptor, bytes) of this rank's rows; only for rows allocated with BANG_B200_SHARD_VMM=1.
+        The caller passes the descriptor to its peers (sharding.exchange_fds) and closes it."""
+        fd, nbytes = ctypes.c_int(-1), ctypes.c_uint64(0)
+        self._check(self._lib.bang_b200_export_shard_fd(self._h, ctypes.byref(fd), ctypes.byref(nbytes)))
+        return fd.value, int(nbytes.value)
+
+    def import_shard_fd(self, shard: int, fd: int, nbytes: int) -> None:
+        self._check(self._lib.bang_b200_import_shard_fd(self._h, shard, fd, nbytes))
 
     # device-resident load (indices built on the GPUs, too large for files)
     def load_device_begin(self, N: int, D: int, medoid: int, pivots=None, centroid=None, chunk_offsets=None) -> None:

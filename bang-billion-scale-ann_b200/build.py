@@ -68,7 +68,7 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
     cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fopenmp,-O3",
            "-I", INCLUDE, "-I", CSRC, "-o", LIB_CUDA,
            os.path.join(CSRC, "bang_b200.cu"), os.path.join(CSRC, "builder.cu"), os.path.join(CSRC, "loader.cpp"),
-           os.path.join(CSRC, "bang_shim.cpp"),
+           os.path.join(CSRC, "bang_shim.cpp"), os.path.join(CSRC, "shard_mem.cpp"),
            "-lgomp"]
     if verbose_ptxas:
         cmd += ["-Xptxas", "-v"]

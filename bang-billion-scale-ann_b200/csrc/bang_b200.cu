@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "loader.h"
+#include "shard_mem.h"
 #include "search_kernel.cuh"
 
 using namespace bang;
@@ -99,9 +100,10 @@ struct bang_b200_ctx {
   uint32_t D = 0, R = 0, n_chunks = 0;
   uint32_t vec_bytes = 0, vec_units = 0, row_stride = 0, code_stride = 0;
   uint64_t rows_local = 0;
-  uint8_t* d_rows = nullptr;
+  uint8_t* d_rows = nullptr;      // = rows_mem.ptr
+  ShardMem rows_mem;              // this process's shard of the rows (cudaMalloc, or VMM when BANG_B200_SHARD_VMM=1)
   const uint8_t* rows[kMaxShards] = {nullptr};
-  void* imported[kMaxShards] = {nullptr};
+  ShardMem imported[kMaxShards];  // peers' shards mapped into this process
   uint8_t* d_codes = nullptr;
   float* d_pivT = nullptr;
   float* d_piv = nullptr;
@@ -290,7 +292,12 @@ static int load_graph(bang_b200_ctx* c, const std::string& disk_path) {
   c->row_stride = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
   c->rows_local = (c->N + c->n_shards - 1 - c->shard) / c->n_shards;
   const size_t bytes = (size_t)c->rows_local * c->row_stride;
-  CUDA_TRY(cudaMalloc(&c->d_rows, std::max<size_t>(bytes, 256)));
+  {
+    std::string why;
+    const int rc = shard_alloc(&c->rows_mem, bytes, c->device, c->n_shards > 1 && shard_vmm_requested(), &why);
+    if (rc != 0) return set_err(rc == -2 ? BANG_E_NOMEM : BANG_E_CUDA, "rows: " + why);
+    c->d_rows = static_cast<uint8_t*>(c->rows_mem.ptr);
+  }
   c->device_bytes += bytes;
   for (int s = 0; s < kMaxShards; ++s) c->rows[s] = nullptr;
   c->rows[c->shard] = c->d_rows;
@@ -430,8 +437,12 @@ extern "C" int bang_b200_load_device_begin(bang_handle_t c, uint64_t N, uint32_t
   c->row_stride = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
   c->rows_local = (N + c->n_shards - 1 - c->shard) / c->n_shards;
   const size_t bytes = (size_t)c->rows_local * c->row_stride;
-  cudaError_t e = cudaMalloc(&c->d_rows, std::max<size_t>(bytes, 256));
-  if (e != cudaSuccess) { bang_b200_unload(c); return set_err(BANG_E_NOMEM, std::string("rows: ") + cudaGetErrorString(e)); }
+  {
+    std::string why;
+    const int rc = shard_alloc(&c->rows_mem, bytes, c->device, c->n_shards > 1 && shard_vmm_requested(), &why);
+    if (rc != 0) { bang_b200_unload(c); return set_err(rc == -2 ? BANG_E_NOMEM : BANG_E_CUDA, "rows: " + why); }
+    c->d_rows = static_cast<uint8_t*>(c->rows_mem.ptr);
+  }
   c->device_bytes += bytes;
   for (int s = 0; s < kMaxShards; ++s) c->rows[s] = nullptr;
   c->rows[c->shard] = c->d_rows;
@@ -478,9 +489,9 @@ extern "C" int bang_b200_unload(bang_handle_t c) {
   if (!c) return set_err(BANG_E_ARG, "null handle");
   if (!c->loaded) return BANG_OK;
   cudaSetDevice(c->device);
-  for (int s = 0; s < kMaxShards; ++s)
-    if (c->imported[s]) { cudaIpcCloseMemHandle(c->imported[s]); c->imported[s] = nullptr; }
-  cudaFree(c->d_rows); cudaFree(c->d_codes); cudaFree(c->d_pivT); cudaFree(c->d_piv); cudaFree(c->d_centroid); cudaFree(c->d_chunk_off);
+  for (int s = 0; s < kMaxShards; ++s) shard_release(&c->imported[s]);
+  shard_release(&c->rows_mem);
+  cudaFree(c->d_codes); cudaFree(c->d_pivT); cudaFree(c->d_piv); cudaFree(c->d_centroid); cudaFree(c->d_chunk_off);
   c->d_rows = nullptr; c->d_codes = nullptr; c->d_pivT = nullptr; c->d_piv = nullptr; c->d_centroid = nullptr; c->d_chunk_off = nullptr;
   c->loaded = false;
   c->device_bytes = 0;
@@ -491,6 +502,7 @@ extern "C" int bang_b200_export_shard(bang_handle_t c, void* out64) {
   if (!c || !out64) return set_err(BANG_E_ARG, "null argument");
   if (!c->loaded) return set_err(BANG_E_STATE, "load first");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  if (c->rows_mem.vmm) return set_err(BANG_E_STATE, "the rows were allocated with BANG_B200_SHARD_VMM=1: use bang_b200_export_shard_fd");
   cudaIpcMemHandle_t hnd;
   CUDA_TRY(cudaIpcGetMemHandle(&hnd, c->d_rows));
   memcpy(out64, &hnd, 64);
@@ -506,8 +518,31 @@ extern "C" int bang_b200_import_shard(bang_handle_t c, int shard, const void* in
   memcpy(&hnd, in64, 64);
   void* p = nullptr;
   CUDA_TRY(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
-  c->imported[shard] = p;
+  shard_release(&c->imported[shard]);
+  c->imported[shard].ptr = p;
+  c->imported[shard].imported = true;
   c->rows[shard] = (const uint8_t*)p;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_export_shard_fd(bang_handle_t c, int* fd_out, uint64_t* bytes_out) {
+  if (!c || !fd_out || !bytes_out) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded) return set_err(BANG_E_STATE, "load first");
+  std::string why;
+  if (shard_export_fd(&c->rows_mem, fd_out, &why) != 0) return set_err(BANG_E_STATE, why);
+  *bytes_out = c->rows_mem.bytes;
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_import_shard_fd(bang_handle_t c, int shard, int fd, uint64_t bytes) {
+  if (!c || fd < 0) return set_err(BANG_E_ARG, "bad argument");
+  if (!c->loaded) return set_err(BANG_E_STATE, "load first");
+  if (shard < 0 || shard >= c->n_shards || shard == c->shard) return set_err(BANG_E_ARG, "bad shard index");
+  CUDA_TRY(cudaSetDevice(c->device));
+  shard_release(&c->imported[shard]);
+  std::string why;
+  if (shard_import_fd(&c->imported[shard], fd, (size_t)bytes, c->device, &why) != 0) return set_err(BANG_E_CUDA, why);
+  c->rows[shard] = static_cast<const uint8_t*>(c->imported[shard].ptr);
   return BANG_OK;
 }
 

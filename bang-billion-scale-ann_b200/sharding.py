@@ -44,10 +44,70 @@ def gather_rows(a: np.ndarray) -> np.ndarray:
     return np.concatenate(outs, 0)
 
 
+def exchange_fds(fd: int, payload: bytes, rank: int, world: int, tag: str | None = None) -> list:
+    """All-to-all of one open file descriptor per rank between the processes of one box.  Returns a list with, for
+    every peer r != rank, (fd_in_this_process, payload_of_r), and None at index `rank`.  Descriptors cannot travel
+    through torch.distributed; they are sent as SCM_RIGHTS ancillary data over Unix-domain sockets (abstract names,
+    nothing on disk).  Ranks must already be in a process group (used for the barriers and to agree on the names)."""
+    import os
+    import socket
+    import torch.distributed as dist
+    if tag is None:
+        box = [None]
+        if rank == 0:
+            box[0] = f"bang_b200_{os.getpid()}_{os.urandom(4).hex()}"
+        dist.broadcast_object_list(box, src=0)
+        tag = box[0]
+    name = lambda r: "\0" + f"{tag}_{r}"
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(name(rank))
+    srv.listen(world)
+    dist.barrier()                      # every rank listens before anyone connects
+    out = [None] * world
+    try:
+        for r in range(world):          # send mine to every peer ...
+            if r == rank:
+                continue
+            c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            c.connect(name(r))
+            hdr = rank.to_bytes(4, "little") + len(payload).to_bytes(4, "little") + payload
+            socket.send_fds(c, [hdr], [fd])
+            c.close()
+        for _ in range(world - 1):      # ... and receive one from each (connections queue in the listen backlog)
+            conn, _addr = srv.accept()
+            data, fds, _flags, _a = socket.recv_fds(conn, 8 + 4096, 1)
+            while len(data) < 8 or len(data) < 8 + int.from_bytes(data[4:8], "little"):
+                more = conn.recv(4096)
+                if not more:
+                    break
+                data += more
+            conn.close()
+            src = int.from_bytes(data[:4], "little")
+            n = int.from_bytes(data[4:8], "little")
+            out[src] = (fds[0], data[8:8 + n])
+    finally:
+        dist.barrier()
+        srv.close()
+    return out
+
+
 def exchange_shards(search, rank: int, world: int) -> None:
-    """After bang_load on every rank with set_sharding(rank, world): import every peer's graph shard."""
+    """After bang_load on every rank with set_sharding(rank, world): import every peer's graph shard.
+    Legacy scheme: 64-byte CUDA IPC handles through all_gather_object.  BANG_B200_SHARD_VMM=1 (set before the load):
+    the rows are VMM allocations, shared as file descriptors (exchange_fds)."""
+    import os
     import torch.distributed as dist
     if world == 1:
+        return
+    if os.environ.get("BANG_B200_SHARD_VMM", "0") not in ("", "0"):
+        fd, nbytes = search.export_shard_fd()
+        got = exchange_fds(fd, nbytes.to_bytes(8, "little"), rank, world)
+        os.close(fd)
+        for r, item in enumerate(got):
+            if r != rank:
+                pfd, payload = item
+                search.import_shard_fd(r, pfd, int.from_bytes(payload, "little"))
+                os.close(pfd)
         return
     handles = [None] * world
     dist.all_gather_object(handles, search.export_shard())

@@ -71,6 +71,12 @@ int bang_b200_load_files(bang_handle_t h, const char* pq_pivots_bin, const char*
 int bang_b200_set_sharding(bang_handle_t h, int shard, int n_shards);
 int bang_b200_export_shard(bang_handle_t h, void* ipc_handle_64B);
 int bang_b200_import_shard(bang_handle_t h, int shard, const void* ipc_handle_64B);
+/* The same exchange for rows allocated with the CUDA virtual-memory API (BANG_B200_SHARD_VMM=1 in the environment at
+ * load time: cuMemCreate at the device's recommended granularity, mapped with matching alignment on both sides).  The
+ * shard travels as a POSIX file descriptor, which the caller passes between the processes (SCM_RIGHTS over a
+ * Unix-domain socket: bang_b200/sharding.py) and closes after the import. */
+int bang_b200_export_shard_fd(bang_handle_t h, int* fd_out, uint64_t* bytes_out);
+int bang_b200_import_shard_fd(bang_handle_t h, int shard, int fd, uint64_t bytes);
 
 /* Device-resident load (no files): for indices that are built on the GPUs themselves and are too large for the
  * box's disk (SIFT1B-shape: a 388 GB `_disk.bin`).  Same HBM layout and search as bang_b200_load; honours

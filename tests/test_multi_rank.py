@@ -44,7 +44,21 @@ def _worker(rank, world, port, out):
         t = sharding.max_over_ranks([1.0 + rank, 5.0 - rank])
         fs = _FakeSearch(rank)
         sharding.exchange_shards(fs, rank, world)
-        out[rank] = (allr.ravel().tolist(), t, sorted(fs.imported), [fs.imported[k][0] for k in sorted(fs.imported)])
+        # file descriptors between the ranks (the transport of VMM shards): every rank shares an open temp file
+        import tempfile
+        with tempfile.TemporaryFile() as f:
+            f.write(b"shard of rank %d" % rank)
+            f.flush()
+            got = sharding.exchange_fds(f.fileno(), (1000 + rank).to_bytes(8, "little"), rank, world)
+        seen = {}
+        for r, item in enumerate(got):
+            if r == rank:
+                assert item is None
+                continue
+            pfd, payload = item
+            seen[r] = (os.pread(pfd, 64, 0).decode(), int.from_bytes(payload, "little"))
+            os.close(pfd)
+        out[rank] = (allr.ravel().tolist(), t, sorted(fs.imported), [fs.imported[k][0] for k in sorted(fs.imported)], seen)
     finally:
         dist.destroy_process_group()
 
@@ -55,7 +69,8 @@ def test_two_ranks_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     for rank in range(world):
-        allr, t, imp, first_bytes = out[rank]
+        allr, t, imp, first_bytes, seen = out[rank]
+        assert seen == {1 - rank: (f"shard of rank {1 - rank}", 1000 + 1 - rank)}   # the peer's descriptor arrived and is readable
         assert allr == list(range(14))              # rank-ordered concatenation of the per-rank batches
         assert t == [2.0, 5.0]                      # slowest rank
         assert imp == [1 - rank] and first_bytes == [1 - rank]   # imported exactly the peer's shard
