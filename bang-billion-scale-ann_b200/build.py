@@ -76,6 +76,21 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
     return LIB_CUDA
 
 
+def build_variant(name: str, defines: list[str], verbose_ptxas: bool = False) -> str:
+    """Experimental builds of the CUDA library (not loaded by default): libbang_b200_<name>.so compiled with the given
+    -D macros, e.g. build_variant("eager", ["BANG_EAGER_EXACT"]) or build_variant("prof", ["BANG_PHASE_TIMERS"]).
+    Select at run time with BANG_B200_LIB=<path> (api.load_library)."""
+    out = os.path.join(PKG_DIR, f"libbang_b200_{name}.so")
+    cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fopenmp,-O3",
+           *[f"-D{d}" for d in defines], "-I", INCLUDE, "-I", CSRC, "-o", out,
+           os.path.join(CSRC, "bang_b200.cu"), os.path.join(CSRC, "builder.cu"), os.path.join(CSRC, "loader.cpp"),
+           os.path.join(CSRC, "bang_shim.cpp"), os.path.join(CSRC, "shard_mem.cpp"), "-lgomp"]
+    if verbose_ptxas:
+        cmd += ["-Xptxas", "-v"]
+    _run(cmd)
+    return out
+
+
 def build_cli(force: bool = False) -> str:
     src = os.path.join(CSRC, "bang_search_main.cpp")
     if not force and _newer(CLI, [src, LIB_CUDA] + _srcs(INCLUDE)):

@@ -348,6 +348,11 @@ struct QState {
   uint32_t* s_id;    // [kListCap] the admitted ones, sorted by (dist, id)
   float* s_d;
   uint32_t* cand_id; // [cand_cap] expanded-node log (PQ modes)
+#ifdef BANG_EAGER_EXACT
+  uint32_t* tk_d;    // [w_cap] running top-k of the expanded nodes by (exact distance bits, id), replaces the log
+  uint32_t* tk_id;
+  uint4* stage;      // [vec_units] landing zone of the next expanded node's vector (cp.async)
+#endif
   uint64_t pol_stream, pol_keep;  // L2 policies: evict-first (one-touch gathers), evict-last (visited filter)
 };
 
@@ -366,7 +371,12 @@ __host__ __device__ inline size_t warp_private_bytes(int mode, uint32_t D, uint3
   if (mode != kExact) b += align_up((size_t)D * 4, 16);            // qc
   b += align_up(L, 16) * 9;                                         // worklist: dist + id + visited
   b += (size_t)kListCap * 4 * 4;                                    // neighbour list + sorted admitted list
+#ifdef BANG_EAGER_EXACT
+  if (mode != kExact) b += align_up(L, 16) * 8 + (size_t)vec_units * 16;  // running top-k + vector staging
+  (void)cand_cap;
+#else
   if (mode != kExact) b += align_up((size_t)cand_cap * 4, 16);      // candidate log
+#endif
   return align_up(b, 16);
 }
 
@@ -388,6 +398,11 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
   s.s_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
   s.s_d = (float*)(base + o); o += (size_t)kListCap * 4;
   s.cand_id = (uint32_t*)(base + o);
+#ifdef BANG_EAGER_EXACT
+  s.tk_d = (uint32_t*)(base + o); o += wcap * 4;   // (the log is not kept in this build)
+  s.tk_id = (uint32_t*)(base + o); o += wcap * 4;
+  s.stage = (uint4*)(base + o);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -865,6 +880,87 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
   }
 }
 
+#ifdef BANG_EAGER_EXACT
+// ------------------------------------------------------------------------------------------------
+// Experimental build (-DBANG_EAGER_EXACT): stage 5 folded into the hops.  The vector of a node sits in the same HBM
+// row as its adjacency list, so it is requested together with the adjacency prefetch (cp.async into shared memory, no
+// registers held across the merge) and its exact distance is computed right after the node's expansion — same
+// 8-lane order as l2_row_8lane, so the same bits — and inserted into a running top-k by (distance, id).  The k
+// smallest distinct keys of the log are exactly what rerank_and_write extracts, without its dependent gather rounds.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_vec(const SearchArgs& a, const QState& s, uint32_t node) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint8_t* v = row_ptr(a, node) + kAdjBytes;
+  for (uint32_t u = lane; u < a.vec_units; u += 32) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s.stage + u);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(v + (size_t)u * 16) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ float staged_l2(const QState& s, uint32_t units, uint32_t t) {
+  constexpr int E = Elem<T>::kPerUnit;
+  float acc = 0.0f;
+  for (uint32_t u = t; u < units; u += 8) {  // lane t of 8: units t, t+8, ... in ascending order (= l2_row_8lane)
+    const uint4 r = s.stage[u];
+    float f[E];
+    Elem<T>::unpack(r, f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) { const float d = __fsub_rn(f[e], s.q_f[u * E + e]); acc = __fmaf_rn(d, d, acc); }
+  }
+  return tree8(acc);
+}
+
+// tk_d/tk_id: n entries sorted ascending by (distance bits, id), all distinct, capacity k.  Returns the new count.
+__device__ __forceinline__ uint32_t topk_insert(const QState& s, uint32_t k, uint32_t n, uint32_t db, uint32_t id) {
+  const uint32_t lane = threadIdx.x & 31;
+  if (n == k) {  // full: only something strictly better than the worst entry gets in
+    const uint32_t wd = s.tk_d[k - 1], wi = s.tk_id[k - 1];
+    if (db > wd || (db == wd && id >= wi)) return n;
+  }
+  uint32_t pos = 0;
+  bool dup = false;
+  for (uint32_t b = 0; b < n; b += 32) {
+    const uint32_t j = b + lane;
+    bool less = false, eq = false;
+    if (j < n) {
+      const uint32_t d = s.tk_d[j], i = s.tk_id[j];
+      less = d < db || (d == db && i < id);
+      eq = d == db && i == id;
+    }
+    pos += __popc(__ballot_sync(kFull, less));
+    dup = dup || __any_sync(kFull, eq);
+  }
+  if (dup) return n;  // a node logged twice counts once (the selection of rerank_and_write is strict, too)
+  const uint32_t n_new = min(n + 1, k);
+  uint32_t hi = n_new - 1;  // entries [pos, hi) move up by one, 32 at a time from the tail
+  while (hi > pos) {
+    const uint32_t lo = (hi - pos > 32u) ? hi - 32u : pos;
+    const uint32_t j = lo + lane;
+    const bool act = j < hi;
+    uint32_t d = 0, i = 0;
+    if (act) { d = s.tk_d[j]; i = s.tk_id[j]; }
+    __syncwarp();
+    if (act) { s.tk_d[j + 1] = d; s.tk_id[j + 1] = i; }
+    __syncwarp();
+    hi = lo;
+  }
+  if (lane == 0) { s.tk_d[pos] = db; s.tk_id[pos] = id; }
+  __syncwarp();
+  return n_new;
+}
+
+__device__ __forceinline__ void write_topk(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31;
+  __syncwarp();
+  for (uint32_t r = lane; r < a.k; r += 32) {
+    a.out_ids[(size_t)q * a.k + r] = r < n ? (uint64_t)s.tk_id[r] : 0xFFFFFFFFull;
+    a.out_dists[(size_t)q * a.k + r] = r < n ? __uint_as_float(s.tk_d[r]) : 3.402823466e+38f;
+  }
+}
+#endif  // BANG_EAGER_EXACT
+
 // ------------------------------------------------------------------------------------------------
 // the kernel: blockDim.x = 32 * (query warps per CTA)
 // ------------------------------------------------------------------------------------------------
@@ -908,7 +1004,21 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       uint4* b4 = reinterpret_cast<uint4*>(vis);
       for (uint32_t i = lane; i < kVisBlocks; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
     }
+#ifdef BANG_EAGER_EXACT
+    uint32_t tkn = 0, pend_id = a.medoid;
+    bool pending = MODE != kExact;       // the medoid is every query's first candidate (:455-462): its vector is on the way
+    if (MODE != kExact) stage_vec(a, s, a.medoid);
+    auto eager_consume = [&]() {         // exact distance of the node staged last -> running top-k
+      if (!pending) return;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      const float d = staged_l2<T>(s, a.vec_units, lane & 7);
+      tkn = topk_insert(s, a.k, tkn, __shfl_sync(kFull, __float_as_uint(d), 0), pend_id);
+      pending = false;
+    };
+#else
     if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
+#endif
     __syncwarp();
     if (MODE != kExact)
       for (uint32_t j = lane; j < a.D; j += 32) s.qc[j] = __fsub_rn(s.q_f[j], __ldg(a.centroid + j));
@@ -920,9 +1030,18 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
     uint32_t* const dump_row = a.dump_ids ? a.dump_ids + (size_t)q * a.dump_stride : nullptr;
     auto log_parent = [&](uint32_t node) {
       if (lane == 0) {
+#ifndef BANG_EAGER_EXACT
         if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
+#endif
         if (dump_row && ncand < a.dump_stride) dump_row[ncand] = node;
       }
+#ifdef BANG_EAGER_EXACT
+      if (MODE != kExact && ncand < a.cand_cap) {  // (the previous staged node was consumed after its expansion)
+        stage_vec(a, s, node);
+        pend_id = node;
+        pending = true;
+      }
+#endif
       if (ncand < a.cand_cap) ++ncand;
     };
 
@@ -930,6 +1049,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
       uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, true, &deg, pf);
       sum_deg += deg; n_pass += n;
+#ifdef BANG_EAGER_EXACT
+      eager_consume();
+#endif
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
       uint32_t parent = b.id, mark = have ? b.id : 0x01010101u;
@@ -946,6 +1068,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         scan_from = fu == kNone ? ws : fu;
         n = 0;
         if (have) { n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
+#ifdef BANG_EAGER_EXACT
+        eager_consume();
+#endif
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
@@ -966,7 +1091,12 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         pend_nb = n ? admit_count(b.below, n, ws, a.L) : 0u;
         if (iter == a.max_iter - 1) break;
       }
+#ifdef BANG_EAGER_EXACT
+      eager_consume();  // a node logged by the capped last iteration is never expanded, but it is a candidate
+      write_topk(a, s, q, tkn);
+#else
       rerank_and_write<T>(a, s, q, ncand);
+#endif
     } else {
       // ---- BANG_Inmemory / BANG_Exactdistance (A.2', A.2''): { expand(parent) ; merge ; first unvisited } ----
       // The first unvisited entry after the merge is decided before it: the closest new entry if it is
@@ -976,6 +1106,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         const bool first = iter == 1;
         const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, &deg, pf);
         sum_deg += deg; n_pass += n;
+#ifdef BANG_EAGER_EXACT
+        eager_consume();
+#endif
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
         const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
         pf.tick(PT_SCAN);
@@ -1018,7 +1151,12 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
           a.out_dists[(size_t)q * a.k + r] = r < ws ? s.w_d[r] : 3.402823466e+38f;
         }
       } else {
+#ifdef BANG_EAGER_EXACT
+        eager_consume();
+        write_topk(a, s, q, tkn);
+#else
         rerank_and_write<T>(a, s, q, ncand);
+#endif
         pf.tick(PT_RERANK);
       }
     }
