@@ -662,6 +662,11 @@ extern "C" int bang_b200_free(bang_handle_t c) {
   cudaFree(c->d_queries); cudaFree(c->d_ids); cudaFree(c->d_dists); cudaFree(c->d_bloom); cudaFree(c->d_counter);
   cudaFree(c->d_hops); cudaFree(c->d_sumdeg); cudaFree(c->d_npass); cudaFree(c->d_phase); c->d_phase = nullptr;
   cudaFreeHost(c->h_dists);
+  if (c->l2_persist_bytes) {  // hand the L2 set-aside back: other kernels of the process get the whole cache again
+    cudaCtxResetPersistingL2Cache();
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    c->l2_persist_bytes = 0;
+  }
   cudaStreamDestroy(c->stream);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   c->d_queries = nullptr; c->d_ids = nullptr; c->d_dists = nullptr; c->d_bloom = nullptr; c->d_counter = nullptr;
