@@ -624,6 +624,7 @@ extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
     if (max_persist > 0 && max_window > 0 && !getenv("BANG_B200_NO_L2_PERSIST")) {
       size_t want = std::min((size_t)max_persist, c->bloom_bytes);
       if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2_persist_bytes = want;
+      else cudaGetLastError();  // a performance hint only
     }
     if (getenv("BANG_B200_VERBOSE"))
       fprintf(stderr, "[bang_b200] bloom %zu MiB, L2 persisting max %d MiB window max %d MiB -> persisting %zu MiB\n",
@@ -665,6 +666,7 @@ extern "C" int bang_b200_free(bang_handle_t c) {
   if (c->l2_persist_bytes) {  // hand the L2 set-aside back: other kernels of the process get the whole cache again
     cudaCtxResetPersistingL2Cache();
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+    cudaGetLastError();  // both are hints: a refusal must not surface as the next launch's error
     c->l2_persist_bytes = 0;
   }
   cudaStreamDestroy(c->stream);
@@ -690,7 +692,7 @@ static void apply_l2_window(const bang_b200_ctx* c, cudaStream_t st) {
   v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_bytes / (double)std::max<size_t>(1, v.accessPolicyWindow.num_bytes));
   v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();  // a hint only
 }
 
 static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists) {
