@@ -105,3 +105,27 @@ def test_gpu_builder_graph_is_searchable(tmp_path):
     ids, _ = s.bang_query(q)
     assert recall.calculate_recall(gi, gd, ids, 10) >= 97.0
     s.bang_free(); s.bang_unload()
+
+
+@pytest.mark.parametrize("mode", ["base", "inmemory", "exact"])
+def test_degenerate_graphs_match_oracle(tmp_path, mode):
+    """Isolated entry point, fewer points than k, a dead end: same ids, distances and filler as the oracle."""
+    import oracle as O
+    import pathological as P
+    from bang_b200 import formats
+    omode = {"base": O.MODE_BASE, "inmemory": O.MODE_INMEMORY, "exact": O.MODE_EXACT}[mode]
+    for name, (base, deg, nbrs, medoid, piv, cen, offs, codes, k, L) in P.cases().items():
+        prefix = str(tmp_path / name)
+        formats.write_index(prefix, base, deg, nbrs, medoid, piv, cen, offs, codes)
+        s = api.BANGSearch("uint8", mode)
+        assert s.bang_load(prefix)
+        s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+        s.bang_set_searchparams(k, L)
+        s.bang_alloc(1); s.bang_init(1)
+        ids, d = s.bang_query(P.QUERY)
+        st = s.last_stats(1)
+        s.bang_free(); s.bang_unload()
+        ox = O.OracleIndex(formats.pack_disk_bin(base, deg, nbrs), "uint8", 4, 64, medoid, codes, piv, cen, offs)
+        oids, od, ost = ox.search(P.QUERY, k, L, mode=omode, stats=True)
+        assert np.array_equal(ids, oids) and np.array_equal(d.view(np.uint32), od.view(np.uint32)), name
+        assert np.array_equal(st["hops"], ost["hops"]) and np.array_equal(st["n_cand"], ost["n_cand"]), name

@@ -173,3 +173,20 @@ def test_sequential_filter_semantics():
     ids, d, st = ox.search(q, 5, 8, mode=O.MODE_EXACT, stats=True)
     assert ids[0].tolist() == [3, 2, 4, 1, 5] and d[0].tolist() == [0.0, 1.0, 1.0, 4.0, 4.0]  # ties by id
     assert st["n_cand"][0] == 65  # medoid + 64 neighbours, every later list is fully filtered
+
+
+@pytest.mark.parametrize("mode", [O.MODE_BASE, O.MODE_INMEMORY, O.MODE_EXACT])
+def test_degenerate_graphs(mode):
+    """Searches that run out of graph return what they reached, in (exact distance, id) order, and fill the remaining
+    ranks with id 0xFFFFFFFF / FLT_MAX (the reference reads uninitialised slots there)."""
+    import pathological as P
+    want = {"isolated_entry": [0], "fewer_points_than_k": [2, 4, 3, 1, 0], "dead_end": [2, 1, 0]}
+    for name, (base, deg, nbrs, medoid, piv, cen, offs, codes, k, L) in P.cases().items():
+        ox = O.OracleIndex(formats.pack_disk_bin(base, deg, nbrs), "uint8", 4, 64, medoid, codes, piv, cen, offs)
+        ids, d, st = ox.search(P.QUERY, k, L, mode=mode, stats=True)
+        n = len(want[name])
+        assert ids[0, :n].tolist() == want[name], name
+        assert (ids[0, n:] == P.NO_ID).all() and (d[0, n:] == np.float32(3.4028234663852886e+38)).all(), name
+        exact = ((base[want[name]].astype(np.float32) - P.QUERY[0].astype(np.float32)) ** 2).sum(1)
+        assert d[0, :n].tolist() == exact.tolist() and np.all(np.diff(d[0, :n]) >= 0), name
+        assert st["hops"][0] == n or mode == O.MODE_EXACT, name     # every reached node was expanded once
