@@ -41,6 +41,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Experimental builds: BANG_EAGER_EXACT folds the re-rank into the hops; BANG_TMA_ROWS additionally
+// fetches every expanded node's whole HBM row (adjacency + vector) with one bulk async copy into shared memory.
+#if defined(BANG_TMA_ROWS) && !defined(BANG_EAGER_EXACT)
+#define BANG_EAGER_EXACT
+#endif
+
 namespace bang {
 
 constexpr int kThreads = 32;            // threads per query = one warp (see the header comment)
@@ -352,6 +358,10 @@ struct QState {
   uint32_t* tk_d;    // [w_cap] running top-k of the expanded nodes by (exact distance bits, id), replaces the log
   uint32_t* tk_id;
   uint4* stage;      // [vec_units] landing zone of the next expanded node's vector (cp.async)
+#ifdef BANG_TMA_ROWS
+  uint8_t* row_stage;  // [256 + vec_units*16] the whole row of the next node to expand (cp.async.bulk); stage = its vector part
+  uint64_t* mbar;      // transaction barrier the bulk copy completes on
+#endif
 #endif
   uint64_t pol_stream, pol_keep;  // L2 policies: evict-first (one-touch gathers), evict-last (visited filter)
 };
@@ -373,6 +383,9 @@ __host__ __device__ inline size_t warp_private_bytes(int mode, uint32_t D, uint3
   b += (size_t)kListCap * 4 * 4;                                    // neighbour list + sorted admitted list
 #ifdef BANG_EAGER_EXACT
   if (mode != kExact) b += align_up(L, 16) * 8 + (size_t)vec_units * 16;  // running top-k + vector staging
+#ifdef BANG_TMA_ROWS
+  if (mode != kExact) b += kAdjBytes + 16;                                  // + adjacency part of the staged row, barrier
+#endif
   (void)cand_cap;
 #else
   if (mode != kExact) b += align_up((size_t)cand_cap * 4, 16);      // candidate log
@@ -401,7 +414,14 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
 #ifdef BANG_EAGER_EXACT
   s.tk_d = (uint32_t*)(base + o); o += wcap * 4;   // (the log is not kept in this build)
   s.tk_id = (uint32_t*)(base + o); o += wcap * 4;
+#ifdef BANG_TMA_ROWS
+  s.row_stage = base + o;
+  s.stage = (uint4*)(base + o + kAdjBytes);
+  o += kAdjBytes + (size_t)a.vec_units * 16;
+  s.mbar = (uint64_t*)(base + o);
+#else
   s.stage = (uint4*)(base + o);
+#endif
 #endif
 }
 
@@ -959,6 +979,39 @@ __device__ __forceinline__ void write_topk(const SearchArgs& a, const QState& s,
     a.out_dists[(size_t)q * a.k + r] = r < n ? __uint_as_float(s.tk_d[r]) : 3.402823466e+38f;
   }
 }
+#ifdef BANG_TMA_ROWS
+// One bulk asynchronous copy (TMA unit, not the load/store pipe) brings the whole row — 256 B of neighbour ids and
+// the vector — of the next node to expand into the warp's staging buffer; completion is signalled on an mbarrier
+// (expect_tx / complete_tx).  Works for local HBM and for peer rows over NVLink alike.
+__device__ __forceinline__ void row_fetch_init(const QState& s) {
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s.mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void row_fetch_issue(const SearchArgs& a, const QState& s, uint32_t node) {
+  __syncwarp();  // every lane is done with the previous contents of the staging buffer
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t bytes = kAdjBytes + a.vec_units * 16;
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s.mbar);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s.row_stage);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(row_ptr(a, node)), "r"(bytes), "r"(mb) : "memory");
+  }
+}
+__device__ __forceinline__ void row_fetch_wait(const QState& s, uint32_t phase) {
+  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s.mbar);
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(mb), "r"(phase) : "memory");
+  } while (!done);
+}
+#endif  // BANG_TMA_ROWS
 #endif  // BANG_EAGER_EXACT
 
 // ------------------------------------------------------------------------------------------------
@@ -983,6 +1036,10 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
   const uint64_t pol_stream = l2_policy_evict_first();
   s.pol_stream = pol_stream;
   s.pol_keep = l2_policy_evict_last();
+#ifdef BANG_TMA_ROWS
+  uint32_t row_phase = 0;
+  if (MODE != kExact) row_fetch_init(s);
+#endif
   // [block areas of all warps of the grid][spill bitmap areas of all warps of the grid]
   uint8_t* vis = reinterpret_cast<uint8_t*>(a.bloom) + ((size_t)blockIdx.x * warps + warp) * kVisBlockBytes;
   uint32_t* vbm = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.bloom) + (size_t)gridDim.x * warps * kVisBlockBytes +
@@ -997,7 +1054,19 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
     Prof pf;
     pf.start();
     // ---- per-query setup: query -> smem, bloom filter cleared ----
+#ifdef BANG_TMA_ROWS
+    uint2 my_nb = make_uint2(kNoNbr, kNoNbr);
+    bool row_inflight = false;
+    if (MODE == kExact) my_nb = fetch_adj(a, a.medoid, pol_stream);
+    else { row_fetch_issue(a, s, a.medoid); row_inflight = true; }
+    auto row_arrived = [&]() {   // PQ modes: wait for the staged row, take this lane's two neighbour ids from it
+      if (MODE == kExact) return;
+      if (row_inflight) { row_fetch_wait(s, row_phase); row_phase ^= 1u; row_inflight = false; }
+      my_nb = *reinterpret_cast<const uint2*>(s.row_stage + 8 * lane);
+    };
+#else
     uint2 my_nb = fetch_adj(a, a.medoid, pol_stream);  // the first hop's adjacency row travels during the setup
+#endif
     __syncwarp();
     load_query<T>(a, q, s.q_f);
     {
@@ -1007,10 +1076,19 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
 #ifdef BANG_EAGER_EXACT
     uint32_t tkn = 0, pend_id = a.medoid;
     bool pending = MODE != kExact;       // the medoid is every query's first candidate (:455-462): its vector is on the way
+#ifndef BANG_TMA_ROWS
     if (MODE != kExact) stage_vec(a, s, a.medoid);
+#endif
     auto eager_consume = [&]() {         // exact distance of the node staged last -> running top-k
+#ifdef BANG_TMA_ROWS
+      // a row requested for a node that the iteration cap keeps from being expanded is still awaited here, so that
+      // the barrier is idle when the next request (or the next query) arms it
+      if (row_inflight) { row_fetch_wait(s, row_phase); row_phase ^= 1u; row_inflight = false; }
+      if (!pending) return;
+#else
       if (!pending) return;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
       __syncwarp();
       const float d = staged_l2<T>(s, a.vec_units, lane & 7);
       tkn = topk_insert(s, a.k, tkn, __shfl_sync(kFull, __float_as_uint(d), 0), pend_id);
@@ -1036,17 +1114,28 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         if (dump_row && ncand < a.dump_stride) dump_row[ncand] = node;
       }
 #ifdef BANG_EAGER_EXACT
+#ifdef BANG_TMA_ROWS
+      if (MODE != kExact) {  // a logged node is the next one to expand: its whole row starts travelling now
+        row_fetch_issue(a, s, node);
+        row_inflight = true;
+        if (ncand < a.cand_cap) { pend_id = node; pending = true; }
+      }
+#else
       if (MODE != kExact && ncand < a.cand_cap) {  // (the previous staged node was consumed after its expansion)
         stage_vec(a, s, node);
         pend_id = node;
         pending = true;
       }
 #endif
+#endif
       if (ncand < a.cand_cap) ++ncand;
     };
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
+#ifdef BANG_TMA_ROWS
+      row_arrived();
+#endif
       uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, true, &deg, pf);
       sum_deg += deg; n_pass += n;
 #ifdef BANG_EAGER_EXACT
@@ -1059,7 +1148,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       uint32_t pend_n = n, pend_nb = min(n, a.L), pend_below = 0, scan_from = 0;
       float pend_maxd = 0.0f;
       while (have || pend_n > 0) {
+#ifndef BANG_TMA_ROWS
         if (have) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
+#endif
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
           ws = merge_worklist(a, s, pend_n, pend_nb, pend_below, pend_maxd, ws, iter == 1, mark, &pos0);
           scan_from = min(scan_from, pos0);
@@ -1067,6 +1158,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
         n = 0;
+#ifdef BANG_TMA_ROWS
+        if (have) row_arrived();
+#endif
         if (have) { n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
 #ifdef BANG_EAGER_EXACT
         eager_consume();
@@ -1104,6 +1198,9 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
+#ifdef BANG_TMA_ROWS
+        row_arrived();
+#endif
         const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, &deg, pf);
         sum_deg += deg; n_pass += n;
 #ifdef BANG_EAGER_EXACT
@@ -1129,7 +1226,11 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         if (!from_new) { if (lane == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
         log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
         const bool capped = iter == a.max_iter - 1;
+#ifdef BANG_TMA_ROWS
+        if (MODE == kExact && !capped) my_nb = fetch_adj(a, parent, pol_stream);
+#else
         if (!capped) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
+#endif
         pf.tick(PT_DECIDE);
         if (nb > 0) {
           ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, first, from_new ? parent : kNone, &pos0);
