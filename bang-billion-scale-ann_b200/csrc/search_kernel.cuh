@@ -203,7 +203,11 @@ __device__ __forceinline__ uint4 ld_nc_u4(const void* p, uint64_t pol) {
 }
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 r;
+#ifdef BANG_PLAIN_ROW_LOADS  // experimental: graph rows (possibly peer memory) through the ordinary coherent load path
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
   return r;
 }
 __device__ __forceinline__ uint32_t ld_nc_u32(const void* p, uint64_t pol) {
@@ -510,8 +514,13 @@ __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, floa
 __device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream) {
   uint2 r;
   const uint8_t* p = row_ptr(a, node) + 8 * (threadIdx.x & 31);
+#ifdef BANG_PLAIN_ROW_LOADS
+  (void)pol_stream;
+  asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+#else
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
                : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_stream));
+#endif
   return r;
 }
 

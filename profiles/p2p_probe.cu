@@ -39,16 +39,24 @@ __global__ void fill_kernel(uint32_t* p, size_t n_words) {
 }
 
 // out[warp] = {cycles in peer waits, cycles in local work, checksum}
+// LD: 0 = plain ld.global (LDG.E.64), 1 = the search kernel's form: ld.global.nc.L1::no_allocate.L2::cache_hint with an
+// evict_first policy (fetch_adj in csrc/search_kernel.cuh)
+template <int LD>
 __global__ void __launch_bounds__(512) probe_kernel(const uint8_t* rows, uint64_t n_rows, const uint4* local, uint32_t n_local16,
                                                     int steps, int local_loads, unsigned long long* out) {
   const uint32_t lane = threadIdx.x & 31, warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   uint32_t state = mix(warp * 2654435761u + 12345u);
   long long t_peer = 0, t_local = 0;
   uint32_t acc = 0;
+  uint64_t pol = 0;
+  if (LD == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   for (int s = 0; s < steps; ++s) {
     const uint64_t row = (((uint64_t)mix(state) << 32) | mix(state ^ 0x9e3779b9u)) % n_rows;
     long long t0 = clock64();
-    const uint2 v = *reinterpret_cast<const uint2*>(rows + row * kRowBytes + lane * 8);
+    uint2 v;
+    const uint8_t* p = rows + row * kRowBytes + lane * 8;
+    if (LD == 1) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    else v = *reinterpret_cast<const uint2*>(p);
     uint32_t x = v.x ^ v.y;
     x = __reduce_xor_sync(0xffffffffu, x);   // the next row depends on the data: one request in flight per warp
     long long t1 = clock64();
@@ -83,6 +91,8 @@ static void fragment_heap(size_t total_free) {
 
 struct Run { const uint8_t* rows; uint64_t n_rows; };
 
+static int g_ldmode = 0;  // P2P_PROBE_LD=1: the search kernel's load form
+
 static void measure(const char* mode, size_t mib, Run r, int warps_per_sm, int steps, int local_loads) {
   CK(cudaSetDevice(0));
   int sms = 0;
@@ -100,7 +110,8 @@ static void measure(const char* mode, size_t mib, Run r, int warps_per_sm, int s
   float best = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {
     CK(cudaEventRecord(e0));
-    probe_kernel<<<ctas, wpc * 32>>>(r.rows, r.n_rows, local, n_local16, steps, local_loads, out);
+    if (g_ldmode) probe_kernel<1><<<ctas, wpc * 32>>>(r.rows, r.n_rows, local, n_local16, steps, local_loads, out);
+    else probe_kernel<0><<<ctas, wpc * 32>>>(r.rows, r.n_rows, local, n_local16, steps, local_loads, out);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
@@ -111,9 +122,9 @@ static void measure(const char* mode, size_t mib, Run r, int warps_per_sm, int s
   CK(cudaMemcpy(h.data(), out, h.size() * 8, cudaMemcpyDeviceToHost));
   double tp = 0, tl = 0;
   for (int w = 0; w < n_warps; ++w) { tp += (double)h[w * 3]; tl += (double)h[w * 3 + 1]; }
-  printf("{\"mode\": \"%s\", \"footprint_mib\": %zu, \"warps_per_sm\": %d, \"steps\": %d, \"local_loads\": %d, \"ms\": %.3f, "
+  printf("{\"mode\": \"%s\", \"ld\": %d, \"footprint_mib\": %zu, \"warps_per_sm\": %d, \"steps\": %d, \"local_loads\": %d, \"ms\": %.3f, "
          "\"rows_per_s\": %.3e, \"peer_wait_cycles\": %.0f, \"local_work_cycles\": %.0f}\n",
-         mode, mib, warps_per_sm, steps, local_loads, best, (double)n_warps * steps / (best * 1e-3), tp / n_warps / steps, tl / n_warps / steps);
+         mode, g_ldmode, mib, warps_per_sm, steps, local_loads, best, (double)n_warps * steps / (best * 1e-3), tp / n_warps / steps, tl / n_warps / steps);
   fflush(stdout);
   cudaFree(local); cudaFree(out);
 }
@@ -125,6 +136,7 @@ int main(int argc, char** argv) {
   for (char* tok = strtok(argv[2], ","); tok; tok = strtok(nullptr, ",")) sizes.push_back((size_t)atoll(tok));
   const int wps = argc > 3 ? atoi(argv[3]) : 16, steps = argc > 4 ? atoi(argv[4]) : 2000, ll = argc > 5 ? atoi(argv[5]) : 4;
   const bool frag = argc > 6 && atoi(argv[6]) != 0;
+  if (const char* e = getenv("P2P_PROBE_LD")) g_ldmode = atoi(e) != 0;
 
   for (size_t mib : sizes) {
     const size_t bytes = mib << 20;

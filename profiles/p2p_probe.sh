@@ -13,6 +13,9 @@ done
 /tmp/p2p_probe peer $S 16 2000 4 1
 /tmp/p2p_probe peer 1648,5860 4           # concurrency dependence
 /tmp/p2p_probe ipc 1648 4
+# the search kernel's load form (ld.global.nc.L1::no_allocate + evict_first hint) instead of a plain load
+P2P_PROBE_LD=1 /tmp/p2p_probe peer $S
+for mib in 732 1648 5860 23438; do P2P_PROBE_LD=1 /tmp/p2p_probe ipc $mib; done
 # then the A/B on the real path (2 GPUs, 9 M points: 13.3 ms in the slow mode, ~7 ms expected):
 #   T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 profiles/c5_run.py 9e6 10000 176"
 #   $T ; BANG_B200_SHARD_VMM=1 $T
