@@ -307,6 +307,8 @@ def test_visited_filter_spill_blocks(tmp_path, mode, L):
     assert np.array_equal(stats["n_cand"], ost["n_cand"]) and np.array_equal(stats["hops"], ost["hops"])
 
 
+@pytest.mark.skipif(not os.environ.get("BANG_B200_UNVERIFIED_TESTS"),
+                    reason="not yet run on a GPU (added after the round's GPU budget was spent); set BANG_B200_UNVERIFIED_TESTS=1")
 def test_inmemory_cli_reports_recall(fx_u8):
     """`bang` with the Inmemory fork's 15-argument command line (parANN.cu:79-93) + medoid and L: same recall as the API."""
     fx = fx_u8
