@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "bang_b200_create", "bang_b200_destroy", "bang_b200_load", "bang_b200_load_files", "bang_b200_set_sharding",
     "bang_b200_export_shard", "bang_b200_import_shard", "bang_b200_export_shard_fd", "bang_b200_import_shard_fd",
     "bang_b200_load_device_begin", "bang_b200_load_device_rows",
-    "bang_b200_load_device_codes", "bang_b200_load_device_end", "bang_b200_set_searchparams", "bang_b200_alloc",
+    "bang_b200_load_device_codes", "bang_b200_load_device_codes_at", "bang_b200_load_device_end", "bang_b200_set_searchparams", "bang_b200_alloc",
     "bang_b200_init", "bang_b200_query", "bang_b200_free", "bang_b200_unload", "bang_b200_set_dists_layout",
     "bang_b200_query_device", "bang_b200_pq_table", "bang_b200_info", "bang_b200_last_stats",
     "bang_b200_last_timing", "bang_b200_last_error", "bang_load_c", "bang_set_searchparams_c", "bang_query_c",
@@ -85,6 +85,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         "bang_b200_load_device_begin": (ci, [vp, u64, u32, u64, u32, vp, vp, vp]),
         "bang_b200_load_device_rows": (ci, [vp, u64, u64, vp, vp]),
         "bang_b200_load_device_codes": (ci, [vp, u64, u64, vp]),
+        "bang_b200_load_device_codes_at": (ci, [vp, vp, u64, vp]),
         "bang_b200_load_device_end": (ci, [vp]),
         "bang_b200_set_searchparams": (ci, [vp, ci, ci, ci]),
         "bang_b200_alloc": (ci, [vp, ci]),
@@ -230,6 +231,10 @@ class BANGSearch:
 
     def load_device_codes(self, first_id: int, n: int, d_codes_ptr: int) -> None:
         self._check(self._lib.bang_b200_load_device_codes(self._h, first_id, n, d_codes_ptr))
+
+    def load_device_codes_at(self, d_ids_ptr: int, n: int, d_codes_ptr: int) -> None:
+        """codes of n nodes whose ids (u32, device) are not consecutive"""
+        self._check(self._lib.bang_b200_load_device_codes_at(self._h, d_ids_ptr, n, d_codes_ptr))
 
     def load_device_end(self) -> None:
         self._check(self._lib.bang_b200_load_device_end(self._h))

@@ -57,6 +57,32 @@ def _hash32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return (x ^ (x >> 15)) & 0x7FFFFFFF
 
 
+def balance_partitions(sizes, G: int) -> torch.Tensor:
+    """Partitions -> GPUs, largest first onto the lightest GPU.  Returns int64 [P] (on the CPU)."""
+    sizes = [float(x) for x in sizes]
+    load = [0.0] * G
+    out = [0] * len(sizes)
+    for p in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
+        g = min(range(G), key=lambda i: (load[i], i))
+        out[p] = g
+        load[g] += sizes[p]
+    return torch.tensor(out, dtype=torch.int64)
+
+
+def assign_ids(owner: torch.Tensor, counts: list, G: int) -> torch.Tensor:
+    """Node ids under partition ownership: the i-th point (in generation order) owned by GPU g gets id i * G + g, so
+    the search library's ownership rule (id mod G, local row id div G) holds without the rows being interleaved by
+    generation order.  owner: int64 [n] for one chunk; counts: running per-GPU totals, updated in place."""
+    ids = torch.empty_like(owner)
+    for g in range(G):
+        msk = owner == g
+        k = int(msk.sum())
+        if k:
+            ids[msk] = (torch.arange(k, device=owner.device, dtype=torch.int64) + counts[g]) * G + g
+        counts[g] += k
+    return ids
+
+
 def merge_lists(adj_own: torch.Tensor, rows: torch.Tensor, new: torch.Tensor, gid_of_row_mul: int, gid_of_row_add: int) -> None:
     """adj_own[rows] <- the 64 smallest-hash members of (adj_own[rows] ∪ new); rows unique within the call.
     Rows that are still empty (the first of a node's two copies) just take the list."""
@@ -86,12 +112,26 @@ def merge_lists(adj_own: torch.Tensor, rows: torch.Tensor, new: torch.Tensor, gi
 
 
 def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries: int, m: int = 32, P_per_rank: int = 4,
-                   chunk: int = 1 << 22, L_build: int = 64, passes: int = 2, seed: int = synth.BASE_SEED):
+                   chunk: int = 1 << 22, L_build: int = 64, passes: int = 2, seed: int = synth.BASE_SEED,
+                   ownership: str = "mod", device=None, build_fn=None, shard_slack: float = 1.30):
     """Builds the sharded index on the GPUs and loads this rank's shard into `search` (an api.BANGSearch with
     set_sharding(rank, world) already called).  Returns (queries_for_this_rank u8 [q][D], gt_ids [n_gt][100] or None
-    on ranks != 0, timings dict)."""
+    on ranks != 0, gt_dists, medoid, timings dict).
+
+    ownership = "mod": node ids are generation order, rows owned by id mod G (every hop is remote with probability
+    (G-1)/G).  ownership = "partition" (experimental, profiles/locality_sim.py): a row is owned by the GPU of its
+    nearest partition centre and ids are assigned so that id mod G is that GPU (assign_ids); the caller should then
+    send every query to `query_home(...)`.  The returned dict T carries "home" (int64 [G*q], the home GPU of every
+    query of the global batch) and "n_virtual" (the id space, G x the largest per-GPU row count) in that mode.
+
+    device / build_fn exist for the CPU dry run of this logic (tests/test_build_sharded.py: gloo, host Vamana builder):
+    build_fn(vectors [n][D], entry, L, passes, seed) -> int32 [n][64] local neighbour ids, -1 = unused."""
     rank, G = dist.get_rank(), dist.get_world_size()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    on_gpu = dev.type == "cuda"
+    mem_gib = (lambda: torch.cuda.memory_allocated() >> 30) if on_gpu else (lambda: 0)
+    if build_fn is None:
+        build_fn = lambda vec, entry, L, passes, seed: build_vamana_gpu(vec, entry, L=L, passes=passes, seed=seed, device_out=True)
     P = P_per_rank * G
     T = {}
     t0 = time.time()
@@ -115,6 +155,12 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
             pc = torch.where(cnt[:, None] > 0, sums / cnt.clamp(min=1)[:, None], pc)
     dist.broadcast(pc, 0)
     pcn = (pc * pc).sum(1)
+    by_part = ownership == "partition"
+    gpu_of_part = None
+    if by_part:
+        lab_c = (pcn[None, :] - 2.0 * (centers @ pc.T)).argmin(1)           # expected partition sizes ~ mixture centres per partition
+        gpu_of_part = balance_partitions(torch.bincount(lab_c, minlength=P).tolist(), G).to(dev)
+        T["home"] = gpu_of_part[(pcn[None, :] - 2.0 * (queries.float() @ pc.T)).argmin(1)].cpu()
     # PQ: rank 0 trains on chunk 0, everyone receives pivots / centroid
     offs = synth.chunk_offsets_even(D, m)
     piv = torch.zeros(256, D, device=dev)
@@ -131,12 +177,14 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
     # ---- pass 1: every rank generates every chunk; keeps its shards' members, its own rows, its share of the GT ----
     t0 = time.time()
     my_shards = [rank + G * j for j in range(P_per_rank)]
-    cap = int(2 * N / P * 1.30) + chunk // 8
+    cap = int(2 * N / P * shard_slack) + chunk // 8   # shard buffers: every point lands in 2 of the P shards
     sh_vec = [torch.empty((cap, D), dtype=torch.uint8, device=dev) for _ in my_shards]
     sh_gid = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in my_shards]
     sh_n = [0] * P_per_rank
-    n_own = (N - rank + G - 1) // G
+    n_own = (N - rank + G - 1) // G if not by_part else int(N / G * max(1.25, shard_slack)) + chunk // 4   # capacity; the count is known after pass 1
     own_vec = torch.empty((n_own, D), dtype=torch.uint8, device=dev)
+    own_cnt = [0] * G
+    gid_all = torch.empty(N, dtype=torch.int32, device=dev) if by_part else None       # new id of every generated point
     best_d = torch.full((n_gt_queries, 100), float("inf"), device=dev)
     best_i = torch.zeros((n_gt_queries, 100), dtype=torch.int64, device=dev)
     med_d, med_i = float("inf"), 0
@@ -144,9 +192,14 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
         n = min(chunk, N - c * chunk)
         x = gen_chunk(centers, c, n, seed)
         xf = x.float()
-        gid = torch.arange(c * chunk, c * chunk + n, device=dev, dtype=torch.int64)
         d2p = pcn[None, :] - 2.0 * (xf @ pc.T)
         top2 = torch.topk(d2p, 2, dim=1, largest=False)[1]
+        if by_part:   # id = (running index among the points of the owning GPU) * G + owning GPU
+            own = gpu_of_part[top2[:, 0]]
+            gid = assign_ids(own, own_cnt, G)
+            gid_all[c * chunk:c * chunk + n] = gid.to(torch.int32)
+        else:
+            gid = torch.arange(c * chunk, c * chunk + n, device=dev, dtype=torch.int64)
         for j, s in enumerate(my_shards):
             sel = ((top2[:, 0] == s) | (top2[:, 1] == s)).nonzero().squeeze(1)
             k = sel.numel()
@@ -155,26 +208,43 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
             sh_vec[j][sh_n[j]:sh_n[j] + k] = x[sel]
             sh_gid[j][sh_n[j]:sh_n[j] + k] = gid[sel].to(torch.int32)
             sh_n[j] += k
-        first = (rank - c * chunk) % G   # first index of this chunk with global id % G == rank
-        mine = x[first::G]
-        lo = (c * chunk + first) // G
-        own_vec[lo:lo + mine.shape[0]] = mine
+        if by_part:
+            msk = own == rank
+            rows_here = gid[msk] // G
+            if rows_here.numel() and int(rows_here.max()) >= n_own:
+                raise RuntimeError(f"rank {rank} owns more rows than its buffer holds ({int(rows_here.max()) + 1} > {n_own})")
+            own_vec[rows_here] = x[msk]
+        else:
+            first = (rank - c * chunk) % G   # first index of this chunk with global id % G == rank
+            mine = x[first::G]
+            lo = (c * chunk + first) // G
+            own_vec[lo:lo + mine.shape[0]] = mine
         dm = ((xf - mean) ** 2).sum(1)
         v, i = dm.min(0)
         if float(v) < med_d:
-            med_d, med_i = float(v), c * chunk + int(i)
+            med_d, med_i = float(v), int(gid[int(i)])
         if c % G == rank and n_gt_queries:
             xn = (xf * xf).sum(1)
             d2 = gt_qn[:, None] + xn[None, :] - 2.0 * (gt_q @ xf.T)   # fp32, exact for uint8 data (all terms < 2^24)
             dd, ii = torch.topk(d2, min(100, n), dim=1, largest=False)
-            cat_d = torch.cat([best_d, dd], 1); cat_i = torch.cat([best_i, ii + c * chunk], 1)
+            cat_d = torch.cat([best_d, dd], 1); cat_i = torch.cat([best_i, gid[ii]], 1)
             sel = torch.topk(cat_d, 100, dim=1, largest=False)[1]
             best_d = torch.gather(cat_d, 1, sel); best_i = torch.gather(cat_i, 1, sel)
             del d2
         del x, xf, d2p, top2, gid
     medoid = med_i
+    n_virtual = N
+    if by_part:   # every rank processed every chunk, so own_cnt is the same everywhere
+        rows_alloc = max(own_cnt)
+        if rows_alloc > n_own:
+            raise RuntimeError(f"a GPU owns {rows_alloc} rows, more than the {n_own}-row buffers")
+        n_own = rows_alloc                      # rows past this rank's own count are holes (no edge points at them)
+        own_vec = own_vec[:n_own]
+        n_virtual = G * rows_alloc
+        T["n_virtual"] = n_virtual
+        log(rank, f"partition ownership: rows per GPU {own_cnt} (id space {n_virtual})")
     T["generate"] = time.time() - t0
-    log(rank, f"pass 1 done in {T['generate']:.1f}s; shard sizes {sh_n}; medoid {medoid}; mem {torch.cuda.memory_allocated() >> 30} GiB")
+    log(rank, f"pass 1 done in {T['generate']:.1f}s; shard sizes {sh_n}; medoid {medoid}; mem {mem_gib()} GiB")
 
     # ground truth: merge the ranks' partial top-100
     gt_ids = gt_d = None
@@ -201,11 +271,12 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
         sample = vec[::stride].float()
         loc_med = int(((sample - sample.mean(0)) ** 2).sum(1).argmin()) * stride   # entry point of the shard graph
         del sample
-        nb = build_vamana_gpu(vec, min(loc_med, ns - 1), L=L_build, passes=passes, seed=s + 1, device_out=True)   # int32 [ns][64] local ids
+        nb = build_fn(vec, min(loc_med, ns - 1), L_build, passes, s + 1)   # int32 [ns][64] local ids
         gidt = sh_gid[j][:ns]
         sh_vec[j] = None
         del vec
-        torch.cuda.synchronize()
+        if on_gpu:
+            torch.cuda.synchronize()
         T["build"] += time.time() - t0
         t0 = time.time()
         owner = (gidt % G).long()
@@ -237,23 +308,26 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
             del send_rows, send_list, recv_rows, recv_list, order
         del nb, owner
         sh_gid[j] = None
-        torch.cuda.empty_cache()
+        if on_gpu:
+            torch.cuda.empty_cache()
         T["exchange"] += time.time() - t0
-        log(rank, f"shard {s}: {ns} points, build {T['build']:.1f}s exchange {T['exchange']:.1f}s (cumulative); mem {torch.cuda.memory_allocated() >> 30} GiB")
+        log(rank, f"shard {s}: {ns} points, build {T['build']:.1f}s exchange {T['exchange']:.1f}s (cumulative); mem {mem_gib()} GiB")
     deg = (adj_own >= 0).sum(1)
     log(rank, f"merged graph: mean degree {float(deg.float().mean()):.2f}, min {int(deg.min())}, full rows {float((deg == 64).float().mean()):.3f}")
 
     # ---- hand the rows and the codes to the search library ----
     t0 = time.time()
     del deg
-    torch.cuda.empty_cache()   # the library allocates with cudaMalloc: hand torch's cached blocks back first (1e9 points: 80 GB needed)
-    search.load_device_begin(N, D, medoid, piv.cpu().numpy(), cen.cpu().numpy(), offs)
+    if on_gpu:
+        torch.cuda.empty_cache()   # the library allocates with cudaMalloc: hand torch's cached blocks back first (1e9 points: 80 GB needed)
+    search.load_device_begin(n_virtual, D, medoid, piv.cpu().numpy(), cen.cpu().numpy(), offs)
     step = 1 << 22
     for a in range(0, n_own, step):
         b = min(n_own, a + step)
         search.load_device_rows(a, b - a, own_vec[a:b].data_ptr(), adj_own[a:b].data_ptr())
     del own_vec, adj_own
-    torch.cuda.empty_cache()
+    if on_gpu:
+        torch.cuda.empty_cache()
     piv_np, cen_np = piv.cpu().numpy(), cen.cpu().numpy()
     for c0 in range(0, n_chunks, G):   # G chunks at a time: every rank encodes one of them, then G broadcasts
         mine = None
@@ -265,10 +339,20 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
             n = min(chunk, N - c * chunk)
             codes = mine if c == c_me else torch.empty((n, m), dtype=torch.uint8, device=dev)
             dist.broadcast(codes, c % G)
-            search.load_device_codes(c * chunk, n, codes.data_ptr())
-        torch.cuda.synchronize()
+            if by_part:   # the chunk's points carry scattered ids
+                search.load_device_codes_at(gid_all[c * chunk:c * chunk + n].data_ptr(), n, codes.data_ptr())
+            else:
+                search.load_device_codes(c * chunk, n, codes.data_ptr())
+        if on_gpu:
+            torch.cuda.synchronize()
         del mine, codes
     search.load_device_end()
     T["load"] = time.time() - t0
-    my_q = queries[rank * n_queries_per_rank:(rank + 1) * n_queries_per_rank].cpu().numpy()
+    if by_part:   # every query goes to the GPU that owns the partition it falls into
+        mine = (T["home"] == rank).nonzero().squeeze(1)
+        T["my_idx"] = mine.numpy()
+        my_q = queries[mine.to(dev)].cpu().numpy()
+    else:
+        T["my_idx"] = np.arange(rank * n_queries_per_rank, (rank + 1) * n_queries_per_rank)
+        my_q = queries[rank * n_queries_per_rank:(rank + 1) * n_queries_per_rank].cpu().numpy()
     return my_q, gt_ids, gt_d, medoid, T

@@ -63,6 +63,20 @@ __global__ void repack_codes_kernel(const uint8_t* __restrict__ src, uint32_t m,
   dst[row * code_stride + p] = c < m ? src[row * m + c] : (uint8_t)0;
 }
 
+// the same permutation for rows with scattered destination ids (bang_b200_load_device_codes_at)
+__global__ void repack_codes_at_kernel(const uint8_t* __restrict__ src, uint32_t m, uint8_t* __restrict__ dst, uint32_t code_stride,
+                                       const uint32_t* __restrict__ ids, uint64_t n_rows, uint64_t N) {
+  const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t row = idx / code_stride;
+  const uint32_t p = (uint32_t)(idx % code_stride);
+  if (row >= n_rows) return;
+  const uint64_t id = ids[row];
+  if (id >= N) return;
+  const uint32_t g = p >> 5, t = (p & 31) >> 2, b = p & 3;
+  const uint32_t c = 32 * g + 8 * b + t;
+  dst[id * code_stride + p] = c < m ? src[row * m + c] : (uint8_t)0;
+}
+
 // device arrays -> HBM rows (bang_b200_load_device_rows): one warp per node
 __global__ void pack_rows_kernel(const uint8_t* __restrict__ vec, uint32_t vec_bytes, const uint32_t* __restrict__ adj,
                                  uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t n) {
@@ -473,6 +487,18 @@ extern "C" int bang_b200_load_device_codes(bang_handle_t c, uint64_t first_id, u
   const uint64_t total = n * c->code_stride;
   repack_codes_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_codes, c->n_chunks, c->d_codes + first_id * c->code_stride,
                                                                 c->code_stride, n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  return BANG_OK;
+}
+
+extern "C" int bang_b200_load_device_codes_at(bang_handle_t c, const uint32_t* d_ids, uint64_t n, const uint8_t* d_codes) {
+  if (!c || !d_codes || !d_ids) return set_err(BANG_E_ARG, "null argument");
+  if (!c->loaded || !c->d_codes) return set_err(BANG_E_STATE, "bang_b200_load_device_begin (PQ mode) first");
+  if (n == 0) return BANG_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t total = n * c->code_stride;
+  repack_codes_at_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_codes, c->n_chunks, c->d_codes, c->code_stride, d_ids, n, c->N);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
   return BANG_OK;

@@ -88,6 +88,8 @@ int bang_b200_load_device_begin(bang_handle_t h, uint64_t N, uint32_t D, uint64_
 int bang_b200_load_device_rows(bang_handle_t h, uint64_t first_local_row, uint64_t n_rows, const void* d_vectors,
                                const uint32_t* d_adj);
 int bang_b200_load_device_codes(bang_handle_t h, uint64_t first_id, uint64_t n, const uint8_t* d_codes);
+/* the same for n nodes with non-consecutive ids: d_ids is a DEVICE array u32[n], d_codes u8[n][n_chunks] in that order */
+int bang_b200_load_device_codes_at(bang_handle_t h, const uint32_t* d_ids, uint64_t n, const uint8_t* d_codes);
 int bang_b200_load_device_end(bang_handle_t h);
 
 /* BANGSearch<T>::bang_set_searchparams (bang.h:60-62, bang_search.cu:562-567) */

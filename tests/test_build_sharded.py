@@ -62,3 +62,30 @@ def test_hash32_range():
     a = torch.arange(0, 10**9, 10**6, dtype=torch.int64)
     h = BS._hash32(a, a.flip(0))
     assert int(h.min()) >= 0 and int(h.max()) < 2**31 and h.unique().numel() > 990
+
+
+def test_partition_ownership_ids():
+    """assign_ids: the i-th point owned by GPU g gets id i*G + g — so `id mod G` is the owner and `id div G` the local
+    row, the rule the search library already uses — consistently across chunks."""
+    G = 4
+    rng = np.random.default_rng(9)
+    counts = [0] * G
+    seen = {}
+    for chunk in range(5):
+        owner = torch.from_numpy(rng.integers(0, G, size=1000))
+        ids = BS.assign_ids(owner, counts, G)
+        assert torch.equal(ids % G, owner)
+        for g in range(G):
+            rows = (ids[owner == g] // G).tolist()
+            start = seen.get(g, 0)
+            assert rows == list(range(start, start + len(rows)))       # dense, in generation order
+            seen[g] = start + len(rows)
+    assert counts == [seen[g] for g in range(G)] and sum(counts) == 5000
+
+
+def test_balance_partitions():
+    sizes = [50, 10, 10, 10, 30, 30, 5, 5, 40, 20, 20, 10]
+    g = BS.balance_partitions(sizes, 4)
+    loads = [sum(s for s, o in zip(sizes, g.tolist()) if o == k) for k in range(4)]
+    assert sorted(set(g.tolist())) == [0, 1, 2, 3] and max(loads) - min(loads) <= 10 and sum(loads) == sum(sizes)
+    assert torch.equal(g, BS.balance_partitions(sizes, 4))             # deterministic: every rank computes the same map
