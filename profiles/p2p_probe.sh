@@ -19,3 +19,4 @@ for mib in 732 1648 5860 23438; do P2P_PROBE_LD=1 /tmp/p2p_probe ipc $mib; done
 # then the A/B on the real path (2 GPUs, 9 M points: 13.3 ms in the slow mode, ~7 ms expected):
 #   T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 profiles/c5_run.py 9e6 10000 176"
 #   $T ; BANG_B200_SHARD_VMM=1 $T
+#   C5_OWNERSHIP=partition $T        # rows owned by their partition's GPU + query routing (profiles/locality_sim.py: ~86-97 % local hops)
