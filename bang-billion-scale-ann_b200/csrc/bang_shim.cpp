@@ -2,6 +2,7 @@
 // Replaces the API shims of the reference (BANG_Base/bang_search.cu:70-135 and the `#if 0` block at
 // :1787-1806); each method is a one-line forward to bang_b200_*.
 #include <cstdio>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -97,9 +98,25 @@ template <typename T>
 void BANGSearch<T>::bang_query(T* query_array, int num_queries, result_ann_t* nearestNeighbours, float* nearestNeighbours_dist) {
   Impl* p = static_cast<Impl*>(m_pImpl);
   static_assert(sizeof(result_ann_t) == sizeof(uint64_t), "result_ann_t is 64-bit");
+  static const bool timers = getenv("BANG_B200_TIMERS") != nullptr;  // run-time stand-in for the reference's -D_TIMERS build
+  const auto t0 = std::chrono::steady_clock::now();
   note(p, p->h ? bang_b200_query(p->h, query_array, num_queries, reinterpret_cast<uint64_t*>(nearestNeighbours), nearestNeighbours_dist)
                : BANG_E_STATE,
        "bang_query");
+  if (timers && p->h) {
+    // The reference prints one line per kernel family (bang_search.cu:1030-1050); here stages (1)-(6) are one fused
+    // launch, so the breakdown is: that launch on the device, and what is left of the wall clock (copies + launch).
+    const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    bang_b200_timing_t tm;
+    if (bang_b200_last_timing(p->h, &tm) == BANG_OK) {
+      printf("(1)-(6) fused search kernel (%u launch, grid %u x %u threads, %u B smem) = %.3f ms\n", tm.launches, tm.grid, tm.block,
+             tm.smem_bytes, tm.kernel_ms);
+      printf("(7) total transfer_time + launch (CPU <--> GPU: %llu B in, %llu B out) = %.3f ms\n", (unsigned long long)tm.h2d_bytes,
+             (unsigned long long)tm.d2h_bytes, wall - tm.kernel_ms);
+      printf("Wall Clock Time = %.3f\nThroughput = %.2f QPS\nThroughput (Exclude Mem Transfers) = %.2f QPS\n", wall,
+             num_queries * 1000.0 / wall, num_queries * 1000.0 / tm.kernel_ms);
+    }
+  }
 }
 
 template <typename T>
