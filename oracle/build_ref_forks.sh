@@ -1,13 +1,17 @@
 #!/bin/bash
-# Builds the reference's Inmemory and Exactdistance forks for ONE fixture, as recall-level pins of those two modes
-# (DESIGN.md §8 item 5).  Not part of __graft_entry__.build() yet: the binaries have not been run on a GPU.
+# Builds the reference's Inmemory and Exactdistance forks for ONE fixture: the id-level pin of those two storage
+# modes (tests/golden/make_ref_forks_golden.py runs the binaries on a GPU box; tests/test_oracle.py compares).
 #
 # The forks compile N, D, MEDOID, INDEX_ENTRY_LEN, the element type, L and the chunk count in (parANN.h) and do not
 # link as shipped, so — unlike oracle/build_ref.sh, which compiles BANG_Base where it lies — this works
 # on a TEMPORARY COPY under /tmp (never inside the repository): the header gets one extra dataset block for the
 # fixture (the Exactdistance fork's own compile.sh fills its header skeleton with sed in the same way), the three BFS
 # hooks the Inmemory fork calls but never defines become empty functions in a separate file, and a one-line
-# boost/dynamic_bitset.hpp stands in for the unused Boost include.  Only binaries go to oracle/_ref/.
+# boost/dynamic_bitset.hpp stands in for the unused Boost include.  The forks print only a recall figure, so the copy
+# also gets ONE added statement: right after the program's own device-to-host copy of the result ids
+# (BANG_Inmemory/parANN.cu:733-734, BANG_Exactdistance/parANN.cu:824-825) the host array `nearestNeighbours`
+# ([k][Q], unsigned) is written to the file named by $BANG_DUMP_IDS.  Nothing on the search path is touched.
+# Only binaries go to oracle/_ref/.
 #
 # usage: oracle/build_ref_forks.sh <tag> <uint8_t|int8_t|float> <N> <D> <medoid> <L> <chunks>
 #   e.g. oracle/build_ref_forks.sh fx_u8 uint8_t 3000 32 1424 32 8
@@ -41,6 +45,12 @@ m = re.search(r"^#define\s+(DATABASE_PLACE_HOLDER|[A-Z0-9]+)\s*\n#define L\s+\S+
 assert m, "dataset selection lines not found"
 s = s[:m.start()] + f"#define BANGFIXTURE\n#define L {L}\n#define CHUNKS {chunks}\n" + block + s[m.end():]
 open("parANN.h", "w").write(s)
+c = open("parANN.cu").read()
+m = re.search(r"gpuErrchk\(cudaMemcpy\(nearestNeighbours, d_nearestNeighbours,[^;]*;\n", c)
+assert m, "result copy not found"
+dump = ('\t{ const char* bang_dump = getenv("BANG_DUMP_IDS"); if (bang_dump) { FILE* bang_fp = fopen(bang_dump, "wb"); '
+        'fwrite(nearestNeighbours, sizeof(unsigned), (size_t)recall_at * numQueries, bang_fp); fclose(bang_fp); } }\n')
+open("parANN.cu", "w").write(c[:m.end()] + dump + c[m.end():])
 EOF
     EXTRA=""
     if grep -q "SetupBFS" parANN.cu && ! grep -q "^void SetupBFS" parANN.cu; then

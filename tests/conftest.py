@@ -29,17 +29,18 @@ def has_gpu() -> bool:
 class Fixture:
     """A committed golden index materialised into the reference's file formats."""
 
-    def __init__(self, name: str, tmpdir: str):
-        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    def __init__(self, name: str, tmpdir: str, pq: str = "", npz: str | None = None):
+        """pq: suffix of the PQ arrays inside the npz (fx_c1 carries a second PQ layout, m = 128, as `*128`)."""
+        z = np.load(os.path.join(GOLDEN, (npz or name) + ".npz"))
         self.name = name
         self.base = z["base"]
         self.deg = z["deg"]
         self.nbrs = z["nbrs"]
         self.medoid = int(z["medoid"])
-        self.pivots = z["pivots"]
-        self.centroid = z["centroid"]
-        self.chunk_offsets = z["chunk_offsets"]
-        self.codes = z["codes"]
+        self.pivots = z["pivots" + pq]
+        self.centroid = z["centroid" + pq]
+        self.chunk_offsets = z["chunk_offsets" + pq]
+        self.codes = z["codes" + pq]
         self.queries = z["queries"]
         self.gt_ids = z["gt_ids"]
         self.gt_dists = z["gt_dists"]
@@ -78,6 +79,18 @@ def fx_f32(fx_dir):
 @pytest.fixture(scope="session")
 def fx_i8(fx_dir):
     return Fixture("fx_i8", fx_dir)
+
+
+@pytest.fixture(scope="session")
+def fx_c1(fx_dir):
+    """C1 (BASELINE config 1): SIFT10K shape — N = 10^4, D = 128 uint8, 100 queries, PQ m = 32."""
+    return Fixture("fx_c1", fx_dir)
+
+
+@pytest.fixture(scope="session")
+def fx_c1m128(fx_dir):
+    """C1 with the reference's SIFT1BSMALL chunk count, m = 128 (BANG_Inmemory/parANN.h:87)."""
+    return Fixture("fx_c1m128", fx_dir, pq="128", npz="fx_c1")
 
 
 @pytest.fixture(scope="session")

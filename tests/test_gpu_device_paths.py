@@ -2,8 +2,7 @@
   * bang_b200_load_device_begin/_rows/_codes/_end (indices handed over in device memory) == bang_load from files,
   * bang_b200_query_device (device queries/results, caller's stream, no sync) == bang_query,
   * the GPU Vamana builder (bang_b200_build_vamana) produces a graph the search reaches high recall on.
-These paths ran on the GPU all round (bench.py, profiles/c5_run.py) but had no test; the tests themselves were written
-after the round's GPU budget was spent, so they are opt-in until they have passed once."""
+These are the paths bench.py times (query_device) and the sharded C5 driver loads through (load_device_*)."""
 import os
 
 import numpy as np
@@ -11,9 +10,7 @@ import pytest
 
 from bang_b200 import api, recall
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("BANG_B200_UNVERIFIED_TESTS"),
-                                 reason="not yet run on a GPU (added after the round's GPU budget was spent); set BANG_B200_UNVERIFIED_TESTS=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _host_search(fx, mode, k, L):

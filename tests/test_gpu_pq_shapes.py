@@ -3,9 +3,7 @@ the CS = 4 kernel): m > 32 (two or more 32-chunk groups per code row — the ref
 parANN.h:101, SIFT10K 128, :87), uneven chunk sizes (CS = 0 kernel) and 3-dim chunks (CS = 3 kernel).
 Same bar as test_gpu_parity: ids, distance bits and counters identical to the oracle.
 
-Written after the round's GPU budget was spent: these cases have not run on a GPU yet, so they are opt-in
-(BANG_B200_UNVERIFIED_TESTS=1) until they have passed once; the oracle side is covered on CPU by
-test_oracle_pq_shapes.py."""
+The oracle side of these shapes is covered on CPU by test_oracle_pq_shapes.py."""
 import os
 
 import numpy as np
@@ -15,9 +13,7 @@ from bang_b200 import api, builder, formats
 
 import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("BANG_B200_UNVERIFIED_TESTS"),
-                                 reason="not yet run on a GPU (added after the round's GPU budget was spent); set BANG_B200_UNVERIFIED_TESTS=1")]
+pytestmark = [pytest.mark.gpu]
 
 MODE_O = {"base": O.MODE_BASE, "inmemory": O.MODE_INMEMORY}
 

@@ -95,6 +95,28 @@ def test_oracle_reproduces_reference_cuda_build(name, L, fixtures):
             assert same >= 0.99, (name, L, order, rep, same)
 
 
+FORK_CASES = [("c1", "fx_c1", 20), ("c1", "fx_c1", 64), ("c1", "fx_c1", 152), ("c1m128", "fx_c1m128", 64),
+              ("f32", "fx_f32", 32), ("i8", "fx_i8", 32)]
+
+
+@pytest.mark.parametrize("fork,mode", [("inmem", O.MODE_INMEMORY), ("exact", O.MODE_EXACT)])
+@pytest.mark.parametrize("case,fxname,L", FORK_CASES)
+def test_oracle_reproduces_reference_forks(fork, mode, case, fxname, L, request):
+    """tests/golden/ref_forks_golden.npz = the ids the reference's OWN Inmemory / Exactdistance programs returned on a
+    B200 (BANG_Inmemory/parANN.cu, BANG_Exactdistance/parANN.cu built by oracle/build_ref_forks.sh for each fixture and L;
+    tests/golden/make_ref_forks_golden.py), including the C1 shape (N = 10^4, D = 128 u8, 100 queries; m = 32 and the
+    reference's m = 128).  Bar (north_star): identical top-k ids on >= 99 % of the queries, every repetition."""
+    g = np.load(os.path.join(GOLDEN, "ref_forks_golden.npz"))
+    fx = request.getfixturevalue(fxname)
+    ox = fx.oracle()
+    for order in (O.ORDER_REF, O.ORDER_GPU):
+        ids, _ = ox.search(fx.queries, 10, L, mode=mode, order=order)
+        for rep in range(3):
+            ref = g[f"ids_{fork}_{case}_L{L}_rep{rep}"].astype(np.uint64)
+            same = (ref == ids).all(1).mean()
+            assert same >= 0.99, (fork, case, L, order, rep, same)
+
+
 @pytest.mark.parametrize("mode", [O.MODE_BASE, O.MODE_INMEMORY, O.MODE_EXACT])
 def test_recall_against_bruteforce(fx_u8, mode):
     fx = fx_u8
