@@ -57,6 +57,32 @@ def _srcs(d: str, exts=(".cu", ".cuh", ".cpp", ".h", ".c")) -> list[str]:
     return out
 
 
+CUDA_SOURCES = ["bang_b200.cu", "builder.cu", "search_inst_u8.cu", "search_inst_i8.cu", "search_inst_f32.cu"]
+HOST_SOURCES = ["loader.cpp", "bang_shim.cpp", "shard_mem.cpp"]
+
+
+def _compile_cuda_lib(out: str, defines: list[str], verbose_ptxas: bool) -> None:
+    """nvcc -c per translation unit, in parallel (the search kernel is instantiated per element type in three of
+    them), then one link step.  Objects go to a scratch directory under build/ (git-ignored)."""
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(PKG_DIR, "build", os.path.basename(out).replace(".so", ""))
+    os.makedirs(objdir, exist_ok=True)
+    common = [*ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-O3", *[f"-D{d}" for d in defines],
+              "-I", INCLUDE, "-I", CSRC]
+    if verbose_ptxas:
+        common += ["-Xptxas", "-v"]
+    objs = []
+    jobs = []
+    for src in CUDA_SOURCES + HOST_SOURCES:
+        obj = os.path.join(objdir, src.rsplit(".", 1)[0] + ".o")
+        objs.append(obj)
+        jobs.append([NVCC, *common, "-c", os.path.join(CSRC, src), "-o", obj])
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        list(ex.map(_run, jobs))
+    _run([NVCC, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", out, *objs, "-lgomp"])
+    shutil.rmtree(objdir, ignore_errors=True)
+
+
 def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
     deps = _srcs(CSRC) + _srcs(INCLUDE)
     if not force and _newer(LIB_CUDA, deps):
@@ -65,29 +91,16 @@ def build_cuda(force: bool = False, verbose_ptxas: bool = False) -> str:
         if os.path.exists(LIB_CUDA):
             return LIB_CUDA
         raise RuntimeError("nvcc not found and libbang_b200.so not prebuilt")
-    cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fopenmp,-O3",
-           "-I", INCLUDE, "-I", CSRC, "-o", LIB_CUDA,
-           os.path.join(CSRC, "bang_b200.cu"), os.path.join(CSRC, "builder.cu"), os.path.join(CSRC, "loader.cpp"),
-           os.path.join(CSRC, "bang_shim.cpp"), os.path.join(CSRC, "shard_mem.cpp"),
-           "-lgomp"]
-    if verbose_ptxas:
-        cmd += ["-Xptxas", "-v"]
-    _run(cmd)
+    _compile_cuda_lib(LIB_CUDA, [], verbose_ptxas)
     return LIB_CUDA
 
 
 def build_variant(name: str, defines: list[str], verbose_ptxas: bool = False) -> str:
-    """Experimental builds of the CUDA library (not loaded by default): libbang_b200_<name>.so compiled with the given
-    -D macros, e.g. build_variant("eager", ["BANG_EAGER_EXACT"]) or build_variant("prof", ["BANG_PHASE_TIMERS"]).
-    Select at run time with BANG_B200_LIB=<path> (api.load_library)."""
+    """Debug / experimental builds of the CUDA library (not loaded by default): libbang_b200_<name>.so compiled with
+    the given -D macros, e.g. build_variant("prof", ["BANG_PHASE_TIMERS"]).  Select at run time with
+    BANG_B200_LIB=<path> (api.load_library)."""
     out = os.path.join(PKG_DIR, f"libbang_b200_{name}.so")
-    cmd = [NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fopenmp,-O3",
-           *[f"-D{d}" for d in defines], "-I", INCLUDE, "-I", CSRC, "-o", out,
-           os.path.join(CSRC, "bang_b200.cu"), os.path.join(CSRC, "builder.cu"), os.path.join(CSRC, "loader.cpp"),
-           os.path.join(CSRC, "bang_shim.cpp"), os.path.join(CSRC, "shard_mem.cpp"), "-lgomp"]
-    if verbose_ptxas:
-        cmd += ["-Xptxas", "-v"]
-    _run(cmd)
+    _compile_cuda_lib(out, defines, verbose_ptxas)
     return out
 
 

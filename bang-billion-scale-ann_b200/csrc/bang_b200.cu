@@ -17,6 +17,7 @@
 #include "loader.h"
 #include "shard_mem.h"
 #include "search_kernel.cuh"
+#include "search_inst.cuh"
 
 using namespace bang;
 
@@ -26,9 +27,26 @@ namespace bang {
 // ------------------------------------------------------------------------------------------------
 // `_disk.bin` entry: [T vec[D]][u32 degree][u32 nbr[R]] (entry_len bytes, unaligned)  ->
 // HBM row: [u32 nbr[64], unused slots = kNoNbr][vec, zero padded to 16 B][pad to row_stride]
+// Adjacency rows are validated while they are repacked (the reference only asserts the first and last entry of
+// the file, bang_search.cu:335-345): a degree above R, a neighbour id >= N, or the same id twice in one row are
+// counted in bad[0..2] and fail the load with BANG_E_FORMAT — the kernel's visited filter tests a whole row
+// against the state before the row (snapshot semantics), so a duplicate would be admitted twice.
+__device__ __forceinline__ void validate_row(uint32_t ida, uint32_t idb, uint64_t N, unsigned long long* bad) {
+  // lane l holds slots l and l+32 (kNoNbr = unused)
+  const uint32_t lane = threadIdx.x & 31;
+  bool range = (ida != kNoNbr && ida >= N) || (idb != kNoNbr && idb >= N);
+  bool dup = ida != kNoNbr && ida == idb;
+  for (int j = 0; j < 32; ++j) {
+    const uint32_t oa = __shfl_sync(0xffffffffu, ida, j), ob = __shfl_sync(0xffffffffu, idb, j);
+    if ((uint32_t)j != lane) dup = dup || (ida != kNoNbr && (ida == oa || ida == ob)) || (idb != kNoNbr && (idb == oa || idb == ob));
+  }
+  if (__any_sync(0xffffffffu, range) && lane == 0) atomicAdd(bad + 1, 1ull);
+  if (__any_sync(0xffffffffu, dup) && lane == 0) atomicAdd(bad + 2, 1ull);
+}
+
 __global__ void repack_rows_kernel(const uint8_t* __restrict__ src, uint64_t entry_len, uint32_t vec_bytes, uint32_t R,
                                    uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t first_id, uint64_t n_ids,
-                                   uint32_t shard, uint32_t n_shards) {
+                                   uint32_t shard, uint32_t n_shards, uint64_t N, unsigned long long* __restrict__ bad) {
   // one warp per node
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -39,15 +57,22 @@ __global__ void repack_rows_kernel(const uint8_t* __restrict__ src, uint64_t ent
   uint8_t* d = dst + (id / n_shards) * (uint64_t)row_stride;
   uint32_t deg = 0;
   for (int b = 0; b < 4; ++b) deg |= (uint32_t)e[vec_bytes + b] << (8 * b);
-  if (deg > R) deg = R;
-  for (uint32_t i = lane; i < (uint32_t)kMaxR; i += 32) {
+  if (deg > R) {
+    if (lane == 0) atomicAdd(bad + 0, 1ull);
+    deg = R;
+  }
+  uint32_t ids[2];
+  for (uint32_t h = 0; h < 2; ++h) {
+    const uint32_t i = lane + 32 * h;
     uint32_t v = kNoNbr;
     if (i < deg) {
       v = 0;
       for (int b = 0; b < 4; ++b) v |= (uint32_t)e[vec_bytes + 4 + 4 * i + b] << (8 * b);
     }
     reinterpret_cast<uint32_t*>(d)[i] = v;
+    ids[h] = v;
   }
+  validate_row(ids[0], ids[1], N, bad);
   for (uint32_t i = lane; i < row_stride - kAdjBytes; i += 32) d[kAdjBytes + i] = i < vec_bytes ? e[i] : (uint8_t)0;
 }
 
@@ -79,12 +104,16 @@ __global__ void repack_codes_at_kernel(const uint8_t* __restrict__ src, uint32_t
 
 // device arrays -> HBM rows (bang_b200_load_device_rows): one warp per node
 __global__ void pack_rows_kernel(const uint8_t* __restrict__ vec, uint32_t vec_bytes, const uint32_t* __restrict__ adj,
-                                 uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t n) {
+                                 uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t n, uint64_t N,
+                                 unsigned long long* __restrict__ bad) {
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (warp >= n) return;
   uint8_t* d = dst + warp * (uint64_t)row_stride;
-  for (uint32_t i = lane; i < (uint32_t)kMaxR; i += 32) reinterpret_cast<uint32_t*>(d)[i] = adj[warp * kMaxR + i];
+  const uint32_t ida = adj[warp * kMaxR + lane], idb = adj[warp * kMaxR + 32 + lane];
+  reinterpret_cast<uint32_t*>(d)[lane] = ida;
+  reinterpret_cast<uint32_t*>(d)[32 + lane] = idb;
+  validate_row(ida, idb, N, bad);
   for (uint32_t i = lane; i < row_stride - kAdjBytes; i += 32) d[kAdjBytes + i] = i < vec_bytes ? vec[warp * vec_bytes + i] : (uint8_t)0;
 }
 
@@ -125,6 +154,9 @@ struct bang_b200_ctx {
   float* d_centroid = nullptr;
   uint32_t* d_chunk_off = nullptr;
   uint64_t device_bytes = 0;
+  unsigned long long* d_bad = nullptr;  // row validation counters: degree > R, id >= N, duplicate id (see validate_row)
+  bool piv_global = false;              // the pivot table does not fit in shared memory: read it from global/L2
+  bool code_prefetch = true;            // speculative L2 prefetch of every neighbour's PQ code row (BANG_B200_CODE_PREFETCH)
   // params
   int k = 0, L = 0, distfn = BANG_DIST_L2, dists_layout = BANG_DISTS_RANK_MAJOR;
   // per-alloc scratch
@@ -138,11 +170,13 @@ struct bang_b200_ctx {
   long long* d_phase = nullptr;
   float* h_dists = nullptr;  // pinned staging for the layout transpose
   cudaStream_t stream = nullptr;
+  uint32_t* d_candlog = nullptr;  // expanded-node logs of the resident query warps (PQ modes)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_busy = nullptr;  // recorded after every launch: the next launch (on any stream) waits for it, because
+  bool busy = false;              // the work counter, the visited filters and the candidate logs are shared scratch
   int grid = 0, ctas_per_sm = 0, warps_per_cta = 0, sm_count = 0;
   size_t smem = 0;
   int lastQ = 0;
-  size_t bloom_bytes = 0, l2_persist_bytes = 0, l2_window_max = 0;
   bang_b200_timing_t timing = {};
 };
 
@@ -151,44 +185,29 @@ static size_t elem_size(int dtype) { return dtype == BANG_DT_FLOAT ? 4 : 1; }
 // ------------------------------------------------------------------------------------------------
 // kernel dispatch
 // ------------------------------------------------------------------------------------------------
-typedef void (*search_fn_t)(const SearchArgs);
-typedef void (*table_fn_t)(const SearchArgs, float*);
-
-template <typename T, int CS>
-static search_fn_t pick_mode(int mode) {
-  switch (mode) {
-    case BANG_MODE_BASE: return bang_search_kernel<T, kBase, CS>;
-    case BANG_MODE_INMEMORY: return bang_search_kernel<T, kInmemory, CS>;
-    default: return bang_search_kernel<T, kExact, 0>;
-  }
-}
-template <typename T>
-static search_fn_t pick_cs(int mode, uint32_t cs) {
-  switch (cs) {
-    case 4: return pick_mode<T, 4>(mode);
-    case 3: return pick_mode<T, 3>(mode);
-    default: return pick_mode<T, 0>(mode);
-  }
-}
-static search_fn_t pick_kernel(int dtype, int mode, uint32_t cs) {
+// The search kernels are instantiated per element type in search_inst_{u8,i8,f32}.cu (compiled in parallel); each
+// of those files exports one lookup function (search_inst.cuh).
+static search_fn_t pick_kernel(int dtype, int mode, uint32_t cs, int warps_per_cta) {
+  const int wpc = wpc_variant(mode, warps_per_cta);
   switch (dtype) {
-    case BANG_DT_FLOAT: return pick_cs<float>(mode, cs);
-    case BANG_DT_INT8: return pick_cs<int8_t>(mode, cs);
-    default: return pick_cs<uint8_t>(mode, cs);
+    case BANG_DT_FLOAT: return search_kernel_f32(mode, cs, wpc);
+    case BANG_DT_INT8: return search_kernel_i8(mode, cs, wpc);
+    default: return search_kernel_u8(mode, cs, wpc);
   }
 }
 static table_fn_t pick_table_kernel(int dtype) {
   switch (dtype) {
-    case BANG_DT_FLOAT: return pq_table_kernel<float>;
-    case BANG_DT_INT8: return pq_table_kernel<int8_t>;
-    default: return pq_table_kernel<uint8_t>;
+    case BANG_DT_FLOAT: return table_kernel_f32();
+    case BANG_DT_INT8: return table_kernel_i8();
+    default: return table_kernel_u8();
   }
 }
-static LaunchGeom geometry_for(const bang_b200_ctx* c, uint32_t L, uint32_t cand_cap, size_t optin, size_t per_sm, int max_warps) {
+static LaunchGeom geometry_for(const bang_b200_ctx* c, uint32_t L, uint32_t cand_cap, size_t optin, size_t per_sm, int max_warps,
+                               bool piv_global) {
   switch (c->dtype) {
-    case BANG_DT_FLOAT: return launch_geometry<float>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps);
-    case BANG_DT_INT8: return launch_geometry<int8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps);
-    default: return launch_geometry<uint8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps);
+    case BANG_DT_FLOAT: return launch_geometry<float>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
+    case BANG_DT_INT8: return launch_geometry<int8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
+    default: return launch_geometry<uint8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
   }
 }
 static uint32_t max_iter_for(int mode, int L) {
@@ -295,6 +314,20 @@ static int stream_file(const std::string& path, uint64_t offset, uint64_t item_b
   return rc;
 }
 
+static int rows_check_begin(bang_b200_ctx* c) {
+  if (!c->d_bad) CUDA_TRY(cudaMalloc(&c->d_bad, 3 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(c->d_bad, 0, 3 * sizeof(unsigned long long)));
+  return BANG_OK;
+}
+static int rows_check_end(bang_b200_ctx* c) {
+  unsigned long long bad[3] = {0, 0, 0};
+  CUDA_TRY(cudaMemcpy(bad, c->d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+  if (bad[0] || bad[1] || bad[2])
+    return set_err(BANG_E_FORMAT, "graph rows are ill-formed: " + std::to_string(bad[0]) + " with degree > R, " + std::to_string(bad[1]) +
+                                      " with a neighbour id >= N, " + std::to_string(bad[2]) + " with a repeated neighbour id");
+  return BANG_OK;
+}
+
 static int load_graph(bang_b200_ctx* c, const std::string& disk_path) {
   uint64_t sz = 0;
   if (!file_size(disk_path, &sz, &g_err)) return BANG_E_IO;
@@ -316,13 +349,16 @@ static int load_graph(bang_b200_ctx* c, const std::string& disk_path) {
   for (int s = 0; s < kMaxShards; ++s) c->rows[s] = nullptr;
   c->rows[c->shard] = c->d_rows;
   bang_b200_ctx* cc = c;
-  return stream_file(disk_path, 0, c->entry_len, c->N, [cc](uint8_t* d_chunk, uint64_t first, uint64_t n) -> int {
+  int rc = rows_check_begin(c);
+  if (rc != BANG_OK) return rc;
+  rc = stream_file(disk_path, 0, c->entry_len, c->N, [cc](uint8_t* d_chunk, uint64_t first, uint64_t n) -> int {
     const uint64_t threads = n * 32;
     repack_rows_kernel<<<(unsigned)((threads + 255) / 256), 256>>>(d_chunk, cc->entry_len, cc->vec_bytes, cc->R, cc->d_rows,
-                                                                   cc->row_stride, first, n, cc->shard, cc->n_shards);
+                                                                   cc->row_stride, first, n, cc->shard, cc->n_shards, cc->N, cc->d_bad);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? BANG_OK : set_err(BANG_E_CUDA, std::string("repack_rows: ") + cudaGetErrorString(e));
   });
+  return rc == BANG_OK ? rows_check_end(c) : rc;
 }
 
 static int load_codes(bang_b200_ctx* c, const std::string& path) {
@@ -379,6 +415,12 @@ extern "C" int bang_b200_load(bang_handle_t c, const char* prefix_c) {
   if (!read_graph_meta(meta, &gm, &g_err)) return BANG_E_IO;
   c->N = gm.N; c->D = gm.D; c->R = gm.R; c->medoid = gm.medoid; c->entry_len = gm.entry_len;
   c->device_bytes = 0;
+  // The metadata's datatype word follows the converter's numbering (bang_preprocess.py:42-51: 0 int8, 1 uint8, 2 float),
+  // the same as bang_dtype_t.  The reference only prints it; here an index of another element type is refused —
+  // int8 and uint8 entries have the same length, so nothing else would notice.
+  if (gm.dtype >= BANG_DT_INT8 && gm.dtype <= BANG_DT_FLOAT && gm.dtype != c->dtype)
+    return set_err(BANG_E_FORMAT, "index element type (metadata datatype " + std::to_string(gm.dtype) + ") differs from the handle's (" +
+                                      std::to_string(c->dtype) + ")");
   int rc = check_common(c);
   if (rc != BANG_OK) return rc;
   if (c->mode != BANG_MODE_EXACTDISTANCE) {
@@ -460,6 +502,8 @@ extern "C" int bang_b200_load_device_begin(bang_handle_t c, uint64_t N, uint32_t
   c->device_bytes += bytes;
   for (int s = 0; s < kMaxShards; ++s) c->rows[s] = nullptr;
   c->rows[c->shard] = c->d_rows;
+  rc = rows_check_begin(c);
+  if (rc != BANG_OK) { std::string k = g_err; bang_b200_unload(c); g_err = k; return rc; }
   return BANG_OK;
 }
 
@@ -472,7 +516,8 @@ extern "C" int bang_b200_load_device_rows(bang_handle_t c, uint64_t first_local_
   CUDA_TRY(cudaSetDevice(c->device));
   const uint64_t threads = n_rows * 32;
   pack_rows_kernel<<<(unsigned)((threads + 255) / 256), 256>>>((const uint8_t*)d_vectors, c->vec_bytes, d_adj,
-                                                             c->d_rows + first_local_row * c->row_stride, c->row_stride, n_rows);
+                                                             c->d_rows + first_local_row * c->row_stride, c->row_stride, n_rows,
+                                                             c->N, c->d_bad);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
   return BANG_OK;
@@ -508,7 +553,9 @@ extern "C" int bang_b200_load_device_end(bang_handle_t c) {
   if (!c) return set_err(BANG_E_ARG, "null handle");
   if (!c->loaded || !c->d_rows) return set_err(BANG_E_STATE, "bang_b200_load_device_begin first");
   CUDA_TRY(cudaDeviceSynchronize());
-  return BANG_OK;
+  const int rc = rows_check_end(c);
+  if (rc != BANG_OK) { std::string k = g_err; bang_b200_unload(c); g_err = k; }
+  return rc;
 }
 
 extern "C" int bang_b200_unload(bang_handle_t c) {
@@ -518,6 +565,7 @@ extern "C" int bang_b200_unload(bang_handle_t c) {
   for (int s = 0; s < kMaxShards; ++s) shard_release(&c->imported[s]);
   shard_release(&c->rows_mem);
   cudaFree(c->d_codes); cudaFree(c->d_pivT); cudaFree(c->d_piv); cudaFree(c->d_centroid); cudaFree(c->d_chunk_off);
+  cudaFree(c->d_bad); c->d_bad = nullptr;
   c->d_rows = nullptr; c->d_codes = nullptr; c->d_pivT = nullptr; c->d_piv = nullptr; c->d_centroid = nullptr; c->d_chunk_off = nullptr;
   c->loaded = false;
   c->device_bytes = 0;
@@ -603,29 +651,28 @@ extern "C" int bang_b200_set_dists_layout(bang_handle_t c, bang_dists_layout_t l
   return BANG_OK;
 }
 
-extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
-  if (!c) return set_err(BANG_E_ARG, "null handle");
-  if (!c->loaded) return set_err(BANG_E_STATE, "bang_load must precede bang_alloc");
-  if (c->k <= 0 || c->L <= 0) return set_err(BANG_E_STATE, "bang_set_searchparams must precede bang_alloc");
-  if (c->allocated) return set_err(BANG_E_STATE, "already allocated; call bang_free first");
-  if (Q <= 0) return set_err(BANG_E_ARG, "numQueries must be positive");
-  for (int s = 0; s < c->n_shards; ++s)
-    if (!c->rows[s]) return set_err(BANG_E_STATE, "graph shard " + std::to_string(s) + " has not been imported");
-  CUDA_TRY(cudaSetDevice(c->device));
+static int alloc_impl(bang_b200_ctx* c, int Q) {
   const uint32_t max_iter = max_iter_for(c->mode, c->L);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4);
   int max_optin = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   CUDA_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
-  // Resident queries per SM: bounded by shared memory, and by default by the L2 share of their bloom
-  // filters (50 KB each, kept in L2: 16 x 148 x 50 KB = 118 MB).  BANG_B200_WARPS_PER_SM overrides.
-  // The Exactdistance mode streams whole vectors and wants bytes in flight: 32 warps per SM (2 CTAs).
-  int max_warps = c->mode == BANG_MODE_EXACTDISTANCE ? 32 : 16;
+  // Resident queries per SM: as many query warps as shared memory and the register file allow (PQ modes: up to 32,
+  // one CTA per SM around one pivot table; Exactdistance: 2 CTAs of 16).  BANG_B200_WARPS_PER_SM overrides.
+  int max_warps = 32;
   if (const char* e = getenv("BANG_B200_WARPS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) max_warps = v; }
-  const LaunchGeom g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps);
+  if (const char* e = getenv("BANG_B200_CODE_PREFETCH")) c->code_prefetch = atoi(e) != 0;
+  // A pivot table that does not fit next to one query's state (256 x D floats: D above ~215) stays in global memory
+  // (L2-resident, read with plain loads by the generic-chunk kernel) instead of being refused.
+  c->piv_global = false;
+  LaunchGeom g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps, false);
+  if (g.warps_per_cta < 1 && c->mode != BANG_MODE_EXACTDISTANCE) {
+    c->piv_global = true;
+    g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps, true);
+  }
   if (g.warps_per_cta < 1)
-    return set_err(BANG_E_UNSUPPORTED, "pivot table (256 x " + std::to_string(c->D) + " floats) + one query's state do not fit in " +
+    return set_err(BANG_E_UNSUPPORTED, "one query's state (D = " + std::to_string(c->D) + ", L = " + std::to_string(c->L) + ") does not fit in " +
                                            std::to_string(max_optin) + " B of shared memory");
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->piv_global ? 0 : c->chunk4, g.warps_per_cta);
   c->smem = g.smem;
   c->warps_per_cta = g.warps_per_cta;
   CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
@@ -635,27 +682,13 @@ extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
   c->ctas_per_sm = std::min(occ, g.ctas_per_sm);
   c->grid = std::min((Q + c->warps_per_cta - 1) / c->warps_per_cta, c->ctas_per_sm * c->sm_count);
   const size_t qbytes = (size_t)Q * c->D * elem_size(c->dtype);
+  const size_t slots = (size_t)c->grid * c->warps_per_cta;  // resident query warps of the whole grid
   CUDA_TRY(cudaMalloc(&c->d_queries, qbytes));
   CUDA_TRY(cudaMalloc(&c->d_ids, (size_t)Q * c->k * sizeof(uint64_t)));
   CUDA_TRY(cudaMalloc(&c->d_dists, (size_t)Q * c->k * sizeof(float)));
-  // [16-byte block areas of all resident warps (hot, kept in L2)][spill bitmaps (touched only by blocks that overflow)]
-  c->bloom_bytes = (size_t)c->grid * c->warps_per_cta * kVisBlockBytes;
-  CUDA_TRY(cudaMalloc(&c->d_bloom, (size_t)c->grid * c->warps_per_cta * kBloomWords * 4));
-  {
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-    c->l2_persist_bytes = 0;
-    c->l2_window_max = (size_t)max_window;
-    if (max_persist > 0 && max_window > 0 && !getenv("BANG_B200_NO_L2_PERSIST")) {
-      size_t want = std::min((size_t)max_persist, c->bloom_bytes);
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2_persist_bytes = want;
-      else cudaGetLastError();  // a performance hint only
-    }
-    if (getenv("BANG_B200_VERBOSE"))
-      fprintf(stderr, "[bang_b200] bloom %zu MiB, L2 persisting max %d MiB window max %d MiB -> persisting %zu MiB\n",
-              c->bloom_bytes >> 20, max_persist >> 20, max_window >> 20, c->l2_persist_bytes >> 20);
-  }
+  // [filter block areas of all resident warps (hot, L2-resident)][spill bitmaps (touched only by blocks that overflow)]
+  CUDA_TRY(cudaMalloc(&c->d_bloom, slots * kBloomWords * 4));
+  if (c->mode != BANG_MODE_EXACTDISTANCE) CUDA_TRY(cudaMalloc(&c->d_candlog, slots * (size_t)(max_iter + 1) * 4));
   CUDA_TRY(cudaMalloc(&c->d_counter, 4));
   CUDA_TRY(cudaMalloc(&c->d_hops, (size_t)Q * 4));
   CUDA_TRY(cudaMalloc(&c->d_sumdeg, (size_t)Q * 4));
@@ -667,9 +700,29 @@ extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&c->ev0));
   CUDA_TRY(cudaEventCreate(&c->ev1));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_busy, cudaEventDisableTiming));
   c->Qcap = Q;
-  c->allocated = true;
   return BANG_OK;
+}
+
+extern "C" int bang_b200_alloc(bang_handle_t c, int Q) {
+  if (!c) return set_err(BANG_E_ARG, "null handle");
+  if (!c->loaded) return set_err(BANG_E_STATE, "bang_load must precede bang_alloc");
+  if (c->k <= 0 || c->L <= 0) return set_err(BANG_E_STATE, "bang_set_searchparams must precede bang_alloc");
+  if (c->allocated) return set_err(BANG_E_STATE, "already allocated; call bang_free first");
+  if (Q <= 0) return set_err(BANG_E_ARG, "numQueries must be positive");
+  for (int s = 0; s < c->n_shards; ++s)
+    if (!c->rows[s]) return set_err(BANG_E_STATE, "graph shard " + std::to_string(s) + " has not been imported");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->allocated = true;  // from here on bang_b200_free releases whatever a failed attempt got hold of
+  const int rc = alloc_impl(c, Q);
+  if (rc != BANG_OK) {
+    const std::string keep = g_err;
+    bang_b200_free(c);
+    cudaGetLastError();
+    g_err = keep;
+  }
+  return rc;
 }
 
 extern "C" int bang_b200_init(bang_handle_t c, int Q) {
@@ -685,19 +738,18 @@ extern "C" int bang_b200_free(bang_handle_t c) {
   if (!c) return set_err(BANG_E_ARG, "null handle");
   if (!c->allocated) return BANG_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  cudaDeviceSynchronize();  // launches on callers' streams (bang_b200_query_device) included
   cudaFree(c->d_queries); cudaFree(c->d_ids); cudaFree(c->d_dists); cudaFree(c->d_bloom); cudaFree(c->d_counter);
+  cudaFree(c->d_candlog);
   cudaFree(c->d_hops); cudaFree(c->d_sumdeg); cudaFree(c->d_npass); cudaFree(c->d_phase); c->d_phase = nullptr;
-  cudaFreeHost(c->h_dists);
-  if (c->l2_persist_bytes) {  // hand the L2 set-aside back: other kernels of the process get the whole cache again
-    cudaCtxResetPersistingL2Cache();
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-    cudaGetLastError();  // both are hints: a refusal must not surface as the next launch's error
-    c->l2_persist_bytes = 0;
-  }
-  cudaStreamDestroy(c->stream);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  if (c->h_dists) cudaFreeHost(c->h_dists);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_busy) cudaEventDestroy(c->ev_busy);
+  cudaGetLastError();
   c->d_queries = nullptr; c->d_ids = nullptr; c->d_dists = nullptr; c->d_bloom = nullptr; c->d_counter = nullptr;
+  c->d_candlog = nullptr; c->ev_busy = nullptr; c->busy = false;
   c->d_hops = c->d_sumdeg = c->d_npass = nullptr; c->h_dists = nullptr; c->stream = nullptr; c->ev0 = c->ev1 = nullptr;
   c->allocated = false;
   c->Qcap = 0;
@@ -707,20 +759,6 @@ extern "C" int bang_b200_free(bang_handle_t c) {
 // ------------------------------------------------------------------------------------------------
 // query
 // ------------------------------------------------------------------------------------------------
-// The bloom filters are the only data re-read during a search: pin them in the persisting part of L2
-// (cudaAccessPolicyWindow) so the one-touch gathers of rows and codes cannot evict them.
-static void apply_l2_window(const bang_b200_ctx* c, cudaStream_t st) {
-  if (!c->l2_persist_bytes || !c->d_bloom) return;
-  cudaStreamAttrValue v;
-  memset(&v, 0, sizeof(v));
-  v.accessPolicyWindow.base_ptr = c->d_bloom;
-  v.accessPolicyWindow.num_bytes = std::min(c->bloom_bytes, c->l2_window_max);
-  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_bytes / (double)std::max<size_t>(1, v.accessPolicyWindow.num_bytes));
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();  // a hint only
-}
-
 static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists) {
   memset(a, 0, sizeof(*a));
   for (int s = 0; s < kMaxShards; ++s) a->rows[s] = c->rows[s];
@@ -747,6 +785,10 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   a->out_ids = d_ids;
   a->out_dists = d_dists;
   a->bloom = c->d_bloom;
+  a->cand_log = c->d_candlog;
+  a->piv_global = c->piv_global ? 1u : 0u;
+  a->code_prefetch = c->code_prefetch ? 1u : 0u;
+  a->stop_on_empty_hop = c->mode == BANG_MODE_EXACTDISTANCE ? 1u : 0u;  // BANG_Exactdistance/parANN.cu:1593-1671 as built
   a->counter = c->d_counter;
   a->st_hops = c->d_hops;
   a->st_sumdeg = c->d_sumdeg;
@@ -757,12 +799,15 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
 static int launch_search(bang_b200_ctx* c, const void* d_queries, int Q, uint64_t* d_ids, float* d_dists, cudaStream_t st) {
   SearchArgs a;
   fill_args(c, &a, d_queries, Q, d_ids, d_dists);
-  apply_l2_window(c, st);
+  // one search in flight per handle: a launch on another stream is ordered after the previous one
+  if (c->busy) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_busy, 0));
   CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4, st));
   const int grid = std::min((Q + c->warps_per_cta - 1) / c->warps_per_cta, c->grid);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->chunk4);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->piv_global ? 0 : c->chunk4, c->warps_per_cta);
   fn<<<grid, c->warps_per_cta * 32, c->smem, st>>>(a);
   CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev_busy, st));
+  c->busy = true;
   c->lastQ = Q;
   c->timing.launches = 1;
   c->timing.grid = grid;

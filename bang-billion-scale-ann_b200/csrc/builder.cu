@@ -14,10 +14,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "bang_b200.h"
 #include "search_kernel.cuh"
+#include "search_inst.cuh"
 
 using namespace bang;
 
@@ -278,7 +280,8 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
   if (max_batch == 0) max_batch = (uint32_t)std::max<uint64_t>(1024, std::min<uint64_t>(N / 50, 65536));
   const uint32_t MB = max_batch;
   // search scratch
-  auto kern = bang_search_kernel<T, kExact, 0>;
+  // the Exactdistance instantiation of the search kernel (search_inst_*.cu)
+  search_fn_t kern = sizeof(T) == 4 ? search_kernel_f32(kExact, 0, 16) : (std::is_signed<T>::value ? search_kernel_i8(kExact, 0, 16) : search_kernel_u8(kExact, 0, 16));
   int max_optin = 0, per_sm = 0;
   B_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   B_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));

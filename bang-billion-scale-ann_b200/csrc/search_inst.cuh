@@ -1,0 +1,38 @@
+// search_inst.cuh — the fused search kernel is instantiated once per element type, each in its own translation unit
+// (search_inst_u8.cu / _i8.cu / _f32.cu: 13 kernels apiece, compiled in parallel by build.py); the host code picks
+// an instantiation through these lookups.
+#pragma once
+#include "search_kernel.cuh"
+
+namespace bang {
+typedef void (*search_fn_t)(const SearchArgs);
+typedef void (*table_fn_t)(const SearchArgs, float*);
+
+// mode: 0 Base / 1 Inmemory / 2 Exactdistance; cs: uniform PQ chunk size 4, 3 or 0 (general); wpc: 16 or 32 (wpc_variant)
+search_fn_t search_kernel_u8(int mode, uint32_t cs, int wpc);
+search_fn_t search_kernel_i8(int mode, uint32_t cs, int wpc);
+search_fn_t search_kernel_f32(int mode, uint32_t cs, int wpc);
+table_fn_t table_kernel_u8();
+table_fn_t table_kernel_i8();
+table_fn_t table_kernel_f32();
+
+#ifdef BANG_INST_T
+template <typename T, int CS, int WPC>
+static search_fn_t inst_mode(int mode) {
+  return mode == kBase ? bang_search_kernel<T, kBase, CS, WPC> : bang_search_kernel<T, kInmemory, CS, WPC>;
+}
+template <typename T, int CS>
+static search_fn_t inst_wpc(int mode, int wpc) {
+  return wpc <= 16 ? inst_mode<T, CS, 16>(mode) : inst_mode<T, CS, 32>(mode);
+}
+template <typename T>
+static search_fn_t inst_lookup(int mode, uint32_t cs, int wpc) {
+  if (mode == kExact) return bang_search_kernel<T, kExact, 0, 16>;
+  switch (cs) {
+    case 4: return inst_wpc<T, 4>(mode, wpc);
+    case 3: return inst_wpc<T, 3>(mode, wpc);
+    default: return inst_wpc<T, 0>(mode, wpc);
+  }
+}
+#endif
+}  // namespace bang

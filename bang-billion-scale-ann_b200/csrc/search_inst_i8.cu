@@ -1,0 +1,8 @@
+// The int8_t instantiations of the fused search kernel and of the stand-alone PQ table kernel (see search_inst.cuh).
+#define BANG_INST_T int8_t
+#include "search_inst.cuh"
+
+namespace bang {
+search_fn_t search_kernel_i8(int mode, uint32_t cs, int wpc) { return inst_lookup<int8_t>(mode, cs, wpc); }
+table_fn_t table_kernel_i8() { return pq_table_kernel<int8_t>; }
+}  // namespace bang

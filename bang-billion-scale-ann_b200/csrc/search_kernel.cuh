@@ -41,29 +41,26 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-// Experimental builds: BANG_EAGER_EXACT folds the re-rank into the hops; BANG_TMA_ROWS additionally
-// fetches every expanded node's whole HBM row (adjacency + vector) with one bulk async copy into shared memory.
-#if defined(BANG_TMA_ROWS) && !defined(BANG_EAGER_EXACT)
-#define BANG_EAGER_EXACT
-#endif
 
 namespace bang {
 
 constexpr int kThreads = 32;            // threads per query = one warp (see the header comment)
-constexpr int kMaxWarpsPerCta = 16;  // 512 threads, 103 registers in the PQ kernels (17-24 warps make ptxas cap at 96 registers and spill: slower, profiles/r1_concurrency.md)
+constexpr int kMaxWarpsPerCta = 32;  // PQ modes: one CTA of up to 32 query warps per SM (kernels compiled for 16 / 24 / 32, see bang_search_kernel)
 constexpr int kMaxR = 64;               // MAX_R, bang_search.cu:35
-constexpr int kListCap = kMaxR + 8;     // medoid + R neighbours, padded
+constexpr int kListCap = kMaxR + 2;     // medoid + R neighbours (65), padded to an even count
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
 // The visited filter has the reference's semantics — a 399887-slot bit array addressed by two hashes — but is
-// stored sparsely: 1569 blocks of 255 slots, each block = 16 bytes holding up to 15 one-byte offsets of its set
-// slots (0xFF = empty) plus a count byte.  A typical search sets a few thousand slots (0.8 % of the array), so 25 KB
-// replace the 50 KB bitmap (and the reference's 400 KB byte array) with identical answers; the filters of all
-// resident queries then fit in L2 next to the PQ codes (ncu: profiles/r1_*).  A block that receives a 16th slot
-// spills into its own 255-bit bitmap (32 bytes, in a separate region that is cleared lazily at the moment of the
-// spill and is otherwise never touched), so the filter stays exact and O(1) for any number of insertions —
-// hard queries on 10^7+ point graphs insert 15-20 thousand slots (profiles/r1_c5.md).
+// stored sparsely: 1569 blocks of 255 slots, each block = 8 bytes holding up to 7 one-byte offsets of its set
+// slots (0xFF = empty) plus a count byte.  A typical search sets a few thousand slots (0.8 % of the array: two per
+// block on average), so 12.5 KB replace the 50 KB bitmap (and the reference's 400 KB byte array) with identical
+// answers; the filters of all resident queries (32 per SM: 59 MB) then stay in L2 next to the PQ codes
+// (profiles/r1_l2_footprint.md, r2_*).  A block that receives an 8th slot spills into its own 255-bit bitmap
+// (32 bytes, in a separate region that is cleared lazily at the moment of the spill and is otherwise never
+// touched), so the filter stays exact and O(1) for any number of insertions — hard queries on 10^7+ point
+// graphs insert 15-20 thousand slots (profiles/r1_c5.md).
 constexpr uint32_t kVisBlocks = (kBfEntries + 254u) / 255u;        // 1569
-constexpr uint32_t kVisBlockBytes = ((kVisBlocks * 16u + 127u) / 128u) * 128u;   // 25216: the 16-byte blocks of one query
+constexpr uint32_t kVisSlotsPerBlock = 7;                           // offsets a block holds before it spills
+constexpr uint32_t kVisBlockBytes = ((kVisBlocks * 8u + 127u) / 128u) * 128u;    // 12672: the 8-byte blocks of one query
 constexpr uint32_t kVisBitmapBytes = ((kVisBlocks * 32u + 127u) / 128u) * 128u;  // 50304: the spill bitmaps of one query
 // One allocation holds [block areas of all resident warps][bitmap areas of all resident warps]; kBloomWords is
 // the per-warp allocation unit in 32-bit words.
@@ -100,6 +97,10 @@ struct SearchArgs {
   uint64_t* out_ids;        // device [Q][k]
   float* out_dists;         // device [Q][k] (query-major)
   uint32_t* bloom;          // device: one sparse visited filter (kBloomWords words) per resident query warp
+  uint32_t* cand_log;       // device: expanded-node log, cand_cap ids per resident query warp (PQ modes; read back by the re-rank)
+  uint32_t piv_global;      // 1: the pivot table stays in global memory (it does not fit in shared memory: D above ~215)
+  uint32_t code_prefetch;   // 1: request the PQ codes of every neighbour towards L2 while the filter is consulted
+  uint32_t stop_on_empty_hop;  // 1 (Exactdistance searches): a hop without new neighbours ends the query, see the kernel; 0 for the index builder
   uint32_t* counter;        // device work counter (zeroed before launch)
   uint32_t* st_hops;        // device [Q] or null
   uint32_t* st_sumdeg;
@@ -226,21 +227,19 @@ __device__ __forceinline__ VisAddr vis_addr(uint32_t pos) {
   const uint32_t blk = __umulhi(pos, 0x80808081u) >> 7;  // pos / 255 (exact for pos < 2^31)
   return (blk << 8) | (pos - blk * 255u);
 }
-__device__ __forceinline__ uint4 vis_ld_block(const uint8_t* vis, VisAddr a, uint64_t pol_keep) {
-  uint4 r;
-  const uint8_t* p = vis + (size_t)(a >> 8) * 16;
-  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol_keep));
+__device__ __forceinline__ uint2 vis_ld_block(const uint8_t* vis, VisAddr a, uint64_t pol_keep) {
+  uint2 r;
+  const uint8_t* p = vis + (size_t)(a >> 8) * 8;
+  asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_keep));
   return r;
 }
-// is the slot set, given its block?  Bytes 0..14 hold offsets of set slots or 0xFF; byte 15 counts insertions.
-__device__ __forceinline__ bool vis_test(const uint32_t* vbm, uint4 blk, VisAddr a) {
+// is the slot set, given its block?  Bytes 0..6 hold offsets of set slots or 0xFF; byte 7 counts insertions.
+__device__ __forceinline__ bool vis_test(const uint32_t* vbm, uint2 blk, VisAddr a) {
   const uint32_t pat = (a & 255u) * 0x01010101u;
   // "does any byte equal off": (x - 0x01..) & ~x & 0x80.. is non-zero iff x has a zero byte (exact for the any-test)
-  const uint32_t x0 = blk.x ^ pat, x1 = blk.y ^ pat, x2 = blk.z ^ pat, x3 = (blk.w ^ pat) | 0xFF000000u;  // byte 15 = count
-  bool found = ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) | ((x3 - 0x01010101u) & ~x3)) &
-                0x80808080u) != 0;
-  if (!found && (blk.w >> 24) > 15u) {  // the block spilled: its bitmap holds the 16th and later slots
+  const uint32_t x0 = blk.x ^ pat, x1 = (blk.y ^ pat) | 0xFF000000u;  // byte 7 = count
+  bool found = ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1)) & 0x80808080u) != 0;
+  if (!found && (blk.y >> 24) > kVisSlotsPerBlock) {  // the block spilled: its bitmap holds the 8th and later slots
     const uint32_t off = a & 255u;
     found = (__ldcg(vbm + (size_t)(a >> 8) * 8 + (off >> 5)) >> (off & 31u)) & 1u;
   }
@@ -248,16 +247,16 @@ __device__ __forceinline__ bool vis_test(const uint32_t* vbm, uint4 blk, VisAddr
 }
 // set a slot (not currently set), in two steps so that nothing waits for the atomic's round trip:
 // vis_reserve bumps the block's count byte with one L2 atomic and returns the old count word; vis_commit, called
-// after the distance computations of the hop, stores the offset byte into the reserved position.  Reservations
-// 15 and up belong to the spill bitmap (vis_spill_*): the one lane that drew number 15 clears the block's bitmap,
-// then, after a warp barrier, every lane with a number >= 15 sets its bit.
+// once the hop's code loads are in flight, stores the offset byte into the reserved position.  Reservations
+// 7 and up belong to the spill bitmap (vis_spill_*): the one lane that drew number 7 clears the block's bitmap,
+// then, after a warp barrier, every lane with a number >= 7 sets its bit.
 __device__ __forceinline__ uint32_t vis_reserve(uint8_t* vis, VisAddr a) {
-  return atomicAdd(reinterpret_cast<uint32_t*>(vis + (size_t)(a >> 8) * 16 + 12), 1u << 24);
+  return atomicAdd(reinterpret_cast<uint32_t*>(vis + (size_t)(a >> 8) * 8 + 4), 1u << 24);
 }
 __device__ __forceinline__ bool vis_commit(uint8_t* vis, uint32_t* vbm, VisAddr a, uint32_t old) {  // true: spilled
   const uint32_t idx = old >> 24;
-  if (idx < 15u) { vis[(size_t)(a >> 8) * 16 + idx] = (uint8_t)(a & 255u); return false; }
-  if (idx == 15u) {
+  if (idx < kVisSlotsPerBlock) { vis[(size_t)(a >> 8) * 8 + idx] = (uint8_t)(a & 255u); return false; }
+  if (idx == kVisSlotsPerBlock) {
     uint4* b = reinterpret_cast<uint4*>(vbm + (size_t)(a >> 8) * 8);
     b[0] = make_uint4(0u, 0u, 0u, 0u);
     b[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -346,66 +345,56 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct QState {
-  const float* piv_s;       // [256][D] pivots (CTA-shared, PQ modes)
+  const float* piv_s;       // [256][D] pivots: the CTA-shared copy, or the global table when it does not fit (PQ modes)
   const uint32_t* coff_s;   // [n_chunks+1] chunk offsets (CTA-shared, PQ modes)
-  float* q_f;        // [vec_units * E] query as fp32, zero padded
-  float* qc;         // [D] query - centroid (PQ modes)
-  float* w_d;        // worklist [w_cap], sorted by distance; the exact distances of stage 5 re-use this block
+  float* q_f;        // [vec_units * E] query as fp32, zero padded (PQ modes: only during the re-rank, in place of qc)
+  float* qc;         // [D] query - centroid (PQ modes, during the traversal)
+  float* w_d;        // worklist [w_cap], sorted by distance
   uint32_t* w_id;
   uint8_t* w_v;      // visited flags
   uint32_t* n_id;    // [kListCap] filtered neighbours of this hop, unordered
   float* n_d;
   uint32_t* s_id;    // [kListCap] the admitted ones, sorted by (dist, id)
   float* s_d;
-  uint32_t* cand_id; // [cand_cap] expanded-node log (PQ modes)
-#ifdef BANG_EAGER_EXACT
-  uint32_t* tk_d;    // [w_cap] running top-k of the expanded nodes by (exact distance bits, id), replaces the log
-  uint32_t* tk_id;
-  uint4* stage;      // [vec_units] landing zone of the next expanded node's vector (cp.async)
-#ifdef BANG_TMA_ROWS
-  uint8_t* row_stage;  // [256 + vec_units*16] the whole row of the next node to expand (cp.async.bulk); stage = its vector part
-  uint64_t* mbar;      // transaction barrier the bulk copy completes on
-#endif
-#endif
+  float* cd;         // [cand_cap] exact distances of the re-rank (PQ modes; over the dead worklist)
+  uint32_t* cid;     // [cand_cap] the re-rank's copy of the expanded-node log (behind cd)
+  uint32_t* cand_id; // [cand_cap] expanded-node log of this warp, in global memory (PQ modes; one store per hop)
   uint64_t pol_stream, pol_keep;  // L2 policies: evict-first (one-touch gathers), evict-last (visited filter)
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // CTA-shared bytes
-__host__ __device__ inline size_t cta_shared_bytes(int mode, uint32_t D, uint32_t n_chunks) {
+__host__ __device__ inline size_t cta_shared_bytes(int mode, uint32_t D, uint32_t n_chunks, bool piv_global) {
   if (mode == kExact) return 0;
-  return align_up((size_t)256 * D * 4, 16) + align_up((size_t)(n_chunks + 1) * 4, 16);
+  return (piv_global ? 0 : align_up((size_t)256 * D * 4, 16)) + align_up((size_t)(n_chunks + 1) * 4, 16);
 }
-// private bytes per warp (= per resident query)
+// Private bytes per warp (= per resident query): [query block][worklist | neighbour lists].  PQ modes keep
+// query - centroid in the query block during the traversal and the fp32 query during the re-rank, whose exact
+// distances and candidate ids reuse the (then dead) worklist + list block; the expanded-node log itself lives in
+// global memory — 3152 B per query at D = 128, L = 176, so that 32 queries fit next to the 128 KB pivot table.
+// Exactdistance keeps the fp32 query throughout.
 template <typename T>
 __host__ __device__ inline size_t warp_private_bytes(int mode, uint32_t D, uint32_t vec_units, uint32_t L, uint32_t cand_cap) {
-  size_t b = 0;
-  b += align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);   // q_f
-  if (mode != kExact) b += align_up((size_t)D * 4, 16);            // qc
-  b += align_up(L, 16) * 9;                                         // worklist: dist + id + visited
-  b += (size_t)kListCap * 4 * 4;                                    // neighbour list + sorted admitted list
-#ifdef BANG_EAGER_EXACT
-  if (mode != kExact) b += align_up(L, 16) * 8 + (size_t)vec_units * 16;  // running top-k + vector staging
-#ifdef BANG_TMA_ROWS
-  if (mode != kExact) b += kAdjBytes + 16;                                  // + adjacency part of the staged row, barrier
-#endif
-  (void)cand_cap;
-#else
-  if (mode != kExact) b += align_up((size_t)cand_cap * 4, 16);      // candidate log
-#endif
-  return align_up(b, 16);
+  const size_t qf = align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);  // >= D * 4
+  size_t walk = align_up(L, 16) * 9 + (size_t)kListCap * 4 * 4;  // worklist (dist + id + visited) + n_id/n_d/s_id/s_d
+  if (mode != kExact && walk < (size_t)cand_cap * 8) walk = (size_t)cand_cap * 8;  // (never the case for cand_cap <= L + 121)
+  return align_up(qf + walk, 16);
 }
 
 template <typename T>
 __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const SearchArgs& a, uint32_t warp) {
   size_t o = 0;
-  s.piv_s = (const float*)(base + o);
-  s.coff_s = (const uint32_t*)(base + align_up((size_t)256 * a.D * 4, 16));
-  o += cta_shared_bytes(mode, a.D, a.n_chunks);
+  const bool pg = a.piv_global != 0;
+  s.piv_s = pg ? a.piv : (const float*)(base + o);
+  s.coff_s = (const uint32_t*)(base + (pg ? 0 : align_up((size_t)256 * a.D * 4, 16)));
+  o += cta_shared_bytes(mode, a.D, a.n_chunks, pg);
   o += (size_t)warp * warp_private_bytes<T>(mode, a.D, a.vec_units, a.L, a.cand_cap);
-  s.q_f = (float*)(base + o); o += align_up((size_t)a.vec_units * Elem<T>::kPerUnit * 4, 16);
-  s.qc = (float*)(base + o); if (mode != kExact) o += align_up((size_t)a.D * 4, 16);
+  s.qc = (float*)(base + o);
+  s.q_f = (float*)(base + o);
+  o += align_up((size_t)a.vec_units * Elem<T>::kPerUnit * 4, 16);
+  s.cd = (float*)(base + o);
+  s.cid = (uint32_t*)(base + o) + a.cand_cap;
   const size_t wcap = align_up(a.L, 16);
   s.w_d = (float*)(base + o); o += wcap * 4;
   s.w_id = (uint32_t*)(base + o); o += wcap * 4;
@@ -413,20 +402,8 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
   s.n_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
   s.n_d = (float*)(base + o); o += (size_t)kListCap * 4;
   s.s_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
-  s.s_d = (float*)(base + o); o += (size_t)kListCap * 4;
-  s.cand_id = (uint32_t*)(base + o);
-#ifdef BANG_EAGER_EXACT
-  s.tk_d = (uint32_t*)(base + o); o += wcap * 4;   // (the log is not kept in this build)
-  s.tk_id = (uint32_t*)(base + o); o += wcap * 4;
-#ifdef BANG_TMA_ROWS
-  s.row_stage = base + o;
-  s.stage = (uint4*)(base + o + kAdjBytes);
-  o += kAdjBytes + (size_t)a.vec_units * 16;
-  s.mbar = (uint64_t*)(base + o);
-#else
-  s.stage = (uint4*)(base + o);
-#endif
-#endif
+  s.s_d = (float*)(base + o);
+  s.cand_id = a.cand_log ? a.cand_log + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.cand_cap : nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,6 +486,13 @@ __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, floa
   const uint32_t n = a.vec_units * Elem<T>::kPerUnit;
   for (uint32_t i = threadIdx.x & 31; i < n; i += 32) q_f[i] = i < a.q_dim ? (float)src[i] : 0.0f;
 }
+// query - centroid (populate_pqDist_par's `query[j] - centroid[j]`, bang_search.cu:1118-1129); a MIPS query is
+// padded with one zero dimension (bang_search.cu:1099-1113)
+template <typename T>
+__device__ __forceinline__ void load_query_residual(const SearchArgs& a, uint32_t q, float* qc) {
+  const T* src = reinterpret_cast<const T*>(a.queries) + (size_t)q * a.q_dim;
+  for (uint32_t j = threadIdx.x & 31; j < a.D; j += 32) qc[j] = __fsub_rn(j < a.q_dim ? (float)src[j] : 0.0f, __ldg(a.centroid + j));
+}
 
 // adjacency prefetch: lane l requests neighbour slots 2l and 2l+1 of `node`'s HBM row (one 256-byte request)
 __device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream) {
@@ -546,6 +530,28 @@ struct Prof {
 };
 #endif
 
+// what one lane has to store into the filter after its reservations: slot addresses, the counts the atomics
+// returned, and a mask (bits 0-3: the lane's own four slots, bits 4-5: the medoid's, first hop, lane 0)
+struct FilterIns { VisAddr a[4]; uint32_t r[4]; VisAddr am[2]; uint32_t rm[2]; uint32_t ins; };
+__device__ __forceinline__ void commit_filter(uint8_t* vis, uint32_t* vbm, const FilterIns& f) {
+  uint32_t spill = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (f.ins & (1u << i)) spill |= vis_commit(vis, vbm, f.a[i], f.r[i]) ? (1u << i) : 0u;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (f.ins & (16u << i)) spill |= vis_commit(vis, vbm, f.am[i], f.rm[i]) ? (16u << i) : 0u;
+  if (__any_sync(kFull, spill != 0)) {  // rare: blocks with more than 7 slots
+    __syncwarp();                       // the freshly spilled blocks' bitmaps are cleared
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (spill & (1u << i)) vis_spill_set(vbm, f.a[i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (spill & (16u << i)) vis_spill_set(vbm, f.am[i]);
+  }
+}
+
 struct VisPos { uint32_t p1, p2; };
 template <int MODE>
 __device__ __forceinline__ VisPos vis_pos(uint32_t id) {
@@ -565,11 +571,13 @@ __device__ __forceinline__ VisPos vis_pos(uint32_t id) {
 //            are permuted at load so lane t's chunks 32g+t, 32g+8+t, 32g+16+t, 32g+24+t are one aligned
 //            32-bit word: one 32-byte sector per candidate per 32 chunks, fully used.
 //   exact    compute_neighborDist_par                 BANG_Exactdistance/parANN.cu:1139-1179
-// Returns the number of accepted candidates; n_id/n_d hold them unordered; *deg_out = degree of the node.
+// Returns the number of accepted candidates; n_id/n_d hold them unordered.  The per-query statistics (sum of the
+// expanded nodes' degrees, number of accepted candidates) are kept by lane 0 in the spare last slots of the
+// n_id / s_id lists (a list holds at most 65 entries).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, int CS>
 __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* vis, uint32_t* vbm, uint2 nb2, bool first,
-                                           uint32_t* deg_out, Prof& pf) {
+                                           Prof& pf) {
   const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
   const uint32_t id0 = nb2.x, id1 = nb2.y;
   const bool v0 = id0 != kNoNbr, v1 = id1 != kNoNbr;
@@ -577,7 +585,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   if (__any_sync(kFull, id0 == 0x12345678u && id1 == 0x9abcdef0u)) printf("");  // forces the adjacency load to complete here
   pf.tick(PT_ADJWAIT);
 #endif
-  if (MODE != kExact) {  // codes of every neighbour towards L2 while the filter is being consulted
+  if (MODE != kExact && a.code_prefetch) {  // codes of every neighbour towards L2 while the filter is being consulted
     if (v0) prefetch_l2(a.codes + (size_t)id0 * a.code_stride);
     if (v1) prefetch_l2(a.codes + (size_t)id1 * a.code_stride);
   }
@@ -592,7 +600,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   uint32_t ins0 = (MODE == kExact) ? 1u : 3u, ins1 = ins0;
   if (!first) {
     bool s01 = false, s02 = false, s11 = false, s12 = false;
-    uint4 b01, b02, b11, b12;
+    uint2 b01, b02, b11, b12;
     if (v0) { b01 = vis_ld_block(vis, a01, s.pol_keep); if (MODE != kExact) b02 = vis_ld_block(vis, a02, s.pol_keep); }
     if (v1) { b11 = vis_ld_block(vis, a11, s.pol_keep); if (MODE != kExact) b12 = vis_ld_block(vis, a12, s.pol_keep); }
     if (v0) { s01 = vis_test(vbm, b01, a01); s02 = (MODE == kExact) ? s01 : vis_test(vbm, b02, a02); }
@@ -635,9 +643,20 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   const uint32_t n = pre + c0 + __popc(m1);
   if (acc0) s.n_id[pre + __popc(m0 & lt)] = id0;
   if (acc1) s.n_id[pre + c0 + __popc(m1 & lt)] = id1;
-  *deg_out = __popc(__ballot_sync(kFull, v0)) + __popc(__ballot_sync(kFull, v1));
+  {
+    const uint32_t deg = __popc(__ballot_sync(kFull, v0)) + __popc(__ballot_sync(kFull, v1));
+    if (lane == 0) { s.n_id[kListCap - 1] += deg; s.s_id[kListCap - 1] += n; }
+  }
   __syncwarp();
   pf.tick(PT_COMPACT);
+  // The reserved filter bytes are stored once the first code loads of the hop are in flight: the atomics were
+  // issued before the compaction and have returned by then, and nothing of the filter phase stays live across
+  // the distance computations.
+  FilterIns fi;
+  fi.a[0] = a01; fi.a[1] = a02; fi.a[2] = a11; fi.a[3] = a12;
+  fi.r[0] = r01; fi.r[1] = r02; fi.r[2] = r11; fi.r[3] = r12;
+  fi.am[0] = am1; fi.am[1] = am2; fi.rm[0] = rm1; fi.rm[1] = rm2;
+  fi.ins = ins0 | (ins1 << 2) | ((first && lane == 0) ? (16u | ((MODE != kExact && am2 != am1) ? 32u : 0u)) : 0u);
   const uint32_t t = lane & 7, g = lane >> 3;  // 4 candidates per pass
   if (MODE == kExact) {
     for (uint32_t k0 = 0; k0 < n; k0 += 8) {  // two rows in flight per lane group
@@ -658,6 +677,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
         w[p] = 0;
         if (k < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[k] * a.code_stride + 4 * t, s.pol_stream);
       }
+      if (k0 == 0) commit_filter(vis, vbm, fi);
 #ifdef BANG_PHASE_TIMERS
       if (__any_sync(kFull, (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x12345678u)) printf("");
       pf.tick(PT_CODEWAIT);
@@ -681,6 +701,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       for (uint32_t gg = 0; gg < groups; gg += 2) {
         const uint32_t wa = ld_nc_u32(row + gg * 32, s.pol_stream);
         const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32, s.pol_stream) : 0u;
+        if (k0 == 0 && gg == 0) commit_filter(vis, vbm, fi);
         sum = adc_group<CS, false>(s, a, wa, gg * 32, t, sum);
         sum = adc_group<CS, false>(s, a, wb, (gg + 1) * 32, t, sum);
       }
@@ -688,28 +709,19 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       if (t == 0 && k < n) s.n_d[k] = sum;
     }
   }
-  // the reserved filter bytes: the atomics have long returned
-  uint32_t spill = 0;
-  if (ins0 & 1u) spill |= vis_commit(vis, vbm, a01, r01) ? 1u : 0u;
-  if (ins0 & 2u) spill |= vis_commit(vis, vbm, a02, r02) ? 2u : 0u;
-  if (ins1 & 1u) spill |= vis_commit(vis, vbm, a11, r11) ? 4u : 0u;
-  if (ins1 & 2u) spill |= vis_commit(vis, vbm, a12, r12) ? 8u : 0u;
-  if (first && lane == 0) {
-    spill |= vis_commit(vis, vbm, am1, rm1) ? 16u : 0u;
-    if (MODE != kExact && am2 != am1) spill |= vis_commit(vis, vbm, am2, rm2) ? 32u : 0u;
-  }
-  if (__any_sync(kFull, spill != 0)) {  // rare: blocks with more than 15 slots
-    __syncwarp();                       // the freshly spilled blocks' bitmaps are cleared
-    if (spill & 1u) vis_spill_set(vbm, a01);
-    if (spill & 2u) vis_spill_set(vbm, a02);
-    if (spill & 4u) vis_spill_set(vbm, a11);
-    if (spill & 8u) vis_spill_set(vbm, a12);
-    if (spill & 16u) vis_spill_set(vbm, am1);
-    if (spill & 32u) vis_spill_set(vbm, am2);
-  }
+  if (MODE == kExact || n == 0) commit_filter(vis, vbm, fi);
   __syncwarp();
   pf.tick(PT_LUT);
   return n;
+}
+
+// lane 0's statistics (kept in the lists' spare slots, see expand) go to global before the re-rank reuses the block
+__device__ __forceinline__ void write_stats(const SearchArgs& a, const QState& s, uint32_t q) {
+  if ((threadIdx.x & 31) == 0) {
+    if (a.st_sumdeg) a.st_sumdeg[q] = s.n_id[kListCap - 1];
+    if (a.st_npass) a.st_npass[q] = s.s_id[kListCap - 1];
+  }
+  __syncwarp();
 }
 
 // (dist, id)-minimum of the unsorted neighbour list (optionally skipping the medoid), the number of
@@ -876,11 +888,15 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
 template <typename T>
 __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31, t = lane & 7, g = lane >> 3;
-  float* cd = s.w_d;  // the worklist block is dead by now; cand_cap floats fit in it (see warp_private_bytes)
+  float* cd = s.cd;       // the worklist block is dead by now: exact distances + a copy of the log go there,
+  uint32_t* cid = s.cid;  // the fp32 query where query - centroid was (see warp_private_bytes)
+  __syncwarp();
+  load_query<T>(a, q, s.q_f);
+  for (uint32_t i = lane; i < n; i += 32) cid[i] = __ldcg(s.cand_id + i);
   __syncwarp();
   for (uint32_t b0 = 0; b0 < n; b0 += 8) {
     const uint32_t i0 = b0 + g, i1 = b0 + 4 + g;
-    const uint32_t id0 = i0 < n ? s.cand_id[i0] : a.medoid, id1 = i1 < n ? s.cand_id[i1] : a.medoid;
+    const uint32_t id0 = i0 < n ? cid[i0] : a.medoid, id1 = i1 < n ? cid[i1] : a.medoid;
     float d0, d1;
     l2_two_rows_8lane<T>(row_ptr(a, id0) + kAdjBytes, row_ptr(a, id1) + kAdjBytes, s.q_f, a.vec_units, t, &d0, &d1);
     if (t == 0 && i0 < n) cd[i0] = d0;
@@ -892,7 +908,7 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
   for (uint32_t r = 0; r < a.k; ++r) {
     uint32_t bd = 0xFFFFFFFFu, bid = kNone;
     for (uint32_t i = lane; i < n; i += 32) {
-      const uint32_t db = __float_as_uint(cd[i]), id = s.cand_id[i];
+      const uint32_t db = __float_as_uint(cd[i]), id = cid[i];
       const bool after = !have_last || db > last_d || (db == last_d && id > last_id);
       if (after && (db < bd || (db == bd && id < bid))) { bd = db; bid = id; }
     }
@@ -909,134 +925,31 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
   }
 }
 
-#ifdef BANG_EAGER_EXACT
-// ------------------------------------------------------------------------------------------------
-// Experimental build (-DBANG_EAGER_EXACT): stage 5 folded into the hops.  The vector of a node sits in the same HBM
-// row as its adjacency list, so it is requested together with the adjacency prefetch (cp.async into shared memory, no
-// registers held across the merge) and its exact distance is computed right after the node's expansion — same
-// 8-lane order as l2_row_8lane, so the same bits — and inserted into a running top-k by (distance, id).  The k
-// smallest distinct keys of the log are exactly what rerank_and_write extracts, without its dependent gather rounds.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_vec(const SearchArgs& a, const QState& s, uint32_t node) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint8_t* v = row_ptr(a, node) + kAdjBytes;
-  for (uint32_t u = lane; u < a.vec_units; u += 32) {
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s.stage + u);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(v + (size_t)u * 16) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-template <typename T>
-__device__ __forceinline__ float staged_l2(const QState& s, uint32_t units, uint32_t t) {
-  constexpr int E = Elem<T>::kPerUnit;
-  float acc = 0.0f;
-  for (uint32_t u = t; u < units; u += 8) {  // lane t of 8: units t, t+8, ... in ascending order (= l2_row_8lane)
-    const uint4 r = s.stage[u];
-    float f[E];
-    Elem<T>::unpack(r, f);
-#pragma unroll
-    for (int e = 0; e < E; ++e) { const float d = __fsub_rn(f[e], s.q_f[u * E + e]); acc = __fmaf_rn(d, d, acc); }
-  }
-  return tree8(acc);
-}
-
-// tk_d/tk_id: n entries sorted ascending by (distance bits, id), all distinct, capacity k.  Returns the new count.
-__device__ __forceinline__ uint32_t topk_insert(const QState& s, uint32_t k, uint32_t n, uint32_t db, uint32_t id) {
-  const uint32_t lane = threadIdx.x & 31;
-  if (n == k) {  // full: only something strictly better than the worst entry gets in
-    const uint32_t wd = s.tk_d[k - 1], wi = s.tk_id[k - 1];
-    if (db > wd || (db == wd && id >= wi)) return n;
-  }
-  uint32_t pos = 0;
-  bool dup = false;
-  for (uint32_t b = 0; b < n; b += 32) {
-    const uint32_t j = b + lane;
-    bool less = false, eq = false;
-    if (j < n) {
-      const uint32_t d = s.tk_d[j], i = s.tk_id[j];
-      less = d < db || (d == db && i < id);
-      eq = d == db && i == id;
-    }
-    pos += __popc(__ballot_sync(kFull, less));
-    dup = dup || __any_sync(kFull, eq);
-  }
-  if (dup) return n;  // a node logged twice counts once (the selection of rerank_and_write is strict, too)
-  const uint32_t n_new = min(n + 1, k);
-  uint32_t hi = n_new - 1;  // entries [pos, hi) move up by one, 32 at a time from the tail
-  while (hi > pos) {
-    const uint32_t lo = (hi - pos > 32u) ? hi - 32u : pos;
-    const uint32_t j = lo + lane;
-    const bool act = j < hi;
-    uint32_t d = 0, i = 0;
-    if (act) { d = s.tk_d[j]; i = s.tk_id[j]; }
-    __syncwarp();
-    if (act) { s.tk_d[j + 1] = d; s.tk_id[j + 1] = i; }
-    __syncwarp();
-    hi = lo;
-  }
-  if (lane == 0) { s.tk_d[pos] = db; s.tk_id[pos] = id; }
-  __syncwarp();
-  return n_new;
-}
-
-__device__ __forceinline__ void write_topk(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
-  const uint32_t lane = threadIdx.x & 31;
-  __syncwarp();
-  for (uint32_t r = lane; r < a.k; r += 32) {
-    a.out_ids[(size_t)q * a.k + r] = r < n ? (uint64_t)s.tk_id[r] : 0xFFFFFFFFull;
-    a.out_dists[(size_t)q * a.k + r] = r < n ? __uint_as_float(s.tk_d[r]) : 3.402823466e+38f;
-  }
-}
-#ifdef BANG_TMA_ROWS
-// One bulk asynchronous copy (TMA unit, not the load/store pipe) brings the whole row — 256 B of neighbour ids and
-// the vector — of the next node to expand into the warp's staging buffer; completion is signalled on an mbarrier
-// (expect_tx / complete_tx).  Works for local HBM and for peer rows over NVLink alike.
-__device__ __forceinline__ void row_fetch_init(const QState& s) {
-  if ((threadIdx.x & 31) == 0) {
-    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s.mbar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void row_fetch_issue(const SearchArgs& a, const QState& s, uint32_t node) {
-  __syncwarp();  // every lane is done with the previous contents of the staging buffer
-  if ((threadIdx.x & 31) == 0) {
-    const uint32_t bytes = kAdjBytes + a.vec_units * 16;
-    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s.mbar);
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s.row_stage);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(row_ptr(a, node)), "r"(bytes), "r"(mb) : "memory");
-  }
-}
-__device__ __forceinline__ void row_fetch_wait(const QState& s, uint32_t phase) {
-  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(s.mbar);
-  uint32_t done;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done) : "r"(mb), "r"(phase) : "memory");
-  } while (!done);
-}
-#endif  // BANG_TMA_ROWS
-#endif  // BANG_EAGER_EXACT
 
 // ------------------------------------------------------------------------------------------------
 // the kernel: blockDim.x = 32 * (query warps per CTA)
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE, int CS>
-__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (CS == 0 ? 1 : 0)) bang_search_kernel(const SearchArgs a) {
+// WPC = query warps per CTA the kernel is compiled for.  PQ modes: one CTA per SM around one pivot table, compiled
+// for up to 32 warps (64 registers per thread) and for up to 16 (128 registers; large D, where few queries fit) —
+// the host runs as many warps as shared memory allows for the index's D and the search's L (launch_geometry),
+// because the search is a chain of dependent memory round trips and throughput follows the number of resident
+// queries (profiles/r1_concurrency.md, r2_concurrency.md).  Exactdistance: 2 CTAs of 16 warps per SM.
+template <typename T, int MODE, int CS, int WPC>
+__global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const uint32_t lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const uint32_t warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);  // (through a shuffle: the compiler then knows it is warp-uniform)
   if (MODE != kExact) {
-    // the pivot table and the chunk offsets, once per CTA, shared by all its query warps
-    float4* dst = reinterpret_cast<float4*>(smem_raw);
-    const float4* src = reinterpret_cast<const float4*>(a.piv);
-    const uint32_t n4 = 256u * a.D / 4u;  // D*256 floats; 256*D*4 bytes is a multiple of 16
-    for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
-    uint32_t* coff = reinterpret_cast<uint32_t*>(smem_raw + align_up((size_t)256 * a.D * 4, 16));
+    // the pivot table (unless it stays in global memory) and the chunk offsets, once per CTA, shared by all its query warps
+    uint8_t* p = smem_raw;
+    if (!a.piv_global) {
+      float4* dst = reinterpret_cast<float4*>(smem_raw);
+      const float4* src = reinterpret_cast<const float4*>(a.piv);
+      const uint32_t n4 = 256u * a.D / 4u;  // D*256 floats; 256*D*4 bytes is a multiple of 16
+      for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+      p += align_up((size_t)256 * a.D * 4, 16);
+    }
+    uint32_t* coff = reinterpret_cast<uint32_t*>(p);
     for (uint32_t i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) coff[i] = a.chunk_off[i];
     __syncthreads();  // the only CTA barrier; from here on the warps never meet again
   }
@@ -1045,10 +958,6 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
   const uint64_t pol_stream = l2_policy_evict_first();
   s.pol_stream = pol_stream;
   s.pol_keep = l2_policy_evict_last();
-#ifdef BANG_TMA_ROWS
-  uint32_t row_phase = 0;
-  if (MODE != kExact) row_fetch_init(s);
-#endif
   // [block areas of all warps of the grid][spill bitmap areas of all warps of the grid]
   uint8_t* vis = reinterpret_cast<uint8_t*>(a.bloom) + ((size_t)blockIdx.x * warps + warp) * kVisBlockBytes;
   uint32_t* vbm = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.bloom) + (size_t)gridDim.x * warps * kVisBlockBytes +
@@ -1063,93 +972,32 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
     Prof pf;
     pf.start();
     // ---- per-query setup: query -> smem, bloom filter cleared ----
-#ifdef BANG_TMA_ROWS
-    uint2 my_nb = make_uint2(kNoNbr, kNoNbr);
-    bool row_inflight = false;
-    if (MODE == kExact) my_nb = fetch_adj(a, a.medoid, pol_stream);
-    else { row_fetch_issue(a, s, a.medoid); row_inflight = true; }
-    auto row_arrived = [&]() {   // PQ modes: wait for the staged row, take this lane's two neighbour ids from it
-      if (MODE == kExact) return;
-      if (row_inflight) { row_fetch_wait(s, row_phase); row_phase ^= 1u; row_inflight = false; }
-      my_nb = *reinterpret_cast<const uint2*>(s.row_stage + 8 * lane);
-    };
-#else
     uint2 my_nb = fetch_adj(a, a.medoid, pol_stream);  // the first hop's adjacency row travels during the setup
-#endif
     __syncwarp();
-    load_query<T>(a, q, s.q_f);
-    {
+    if (MODE == kExact) load_query<T>(a, q, s.q_f);
+    else load_query_residual<T>(a, q, s.qc);
+    {  // empty filter: every offset byte 0xFF, count 0 (two 8-byte blocks per store; the padding blocks are never read)
       uint4* b4 = reinterpret_cast<uint4*>(vis);
-      for (uint32_t i = lane; i < kVisBlocks; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
+      for (uint32_t i = lane; i < (kVisBlocks + 1) / 2; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
     }
-#ifdef BANG_EAGER_EXACT
-    uint32_t tkn = 0, pend_id = a.medoid;
-    bool pending = MODE != kExact;       // the medoid is every query's first candidate (:455-462): its vector is on the way
-#ifndef BANG_TMA_ROWS
-    if (MODE != kExact) stage_vec(a, s, a.medoid);
-#endif
-    auto eager_consume = [&]() {         // exact distance of the node staged last -> running top-k
-#ifdef BANG_TMA_ROWS
-      // a row requested for a node that the iteration cap keeps from being expanded is still awaited here, so that
-      // the barrier is idle when the next request (or the next query) arms it
-      if (row_inflight) { row_fetch_wait(s, row_phase); row_phase ^= 1u; row_inflight = false; }
-      if (!pending) return;
-#else
-      if (!pending) return;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
-      __syncwarp();
-      const float d = staged_l2<T>(s, a.vec_units, lane & 7);
-      tkn = topk_insert(s, a.k, tkn, __shfl_sync(kFull, __float_as_uint(d), 0), pend_id);
-      pending = false;
-    };
-#else
     if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
-#endif
-    __syncwarp();
-    if (MODE != kExact)
-      for (uint32_t j = lane; j < a.D; j += 32) s.qc[j] = __fsub_rn(s.q_f[j], __ldg(a.centroid + j));
     __syncwarp();
     __threadfence_block();  // the cleared filter is ordered before this query's tests and insertions
     pf.tick(PT_SETUP);
 
-    uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1, sum_deg = 0, n_pass = 0, deg = 0, pos0 = 0;
-    uint32_t* const dump_row = a.dump_ids ? a.dump_ids + (size_t)q * a.dump_stride : nullptr;
+    uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1, pos0 = 0;
+    if (lane == 0) { s.n_id[kListCap - 1] = 0; s.s_id[kListCap - 1] = 0; }  // statistics (see expand)
     auto log_parent = [&](uint32_t node) {
       if (lane == 0) {
-#ifndef BANG_EAGER_EXACT
         if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
-#endif
-        if (dump_row && ncand < a.dump_stride) dump_row[ncand] = node;
+        if (a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = node;
       }
-#ifdef BANG_EAGER_EXACT
-#ifdef BANG_TMA_ROWS
-      if (MODE != kExact) {  // a logged node is the next one to expand: its whole row starts travelling now
-        row_fetch_issue(a, s, node);
-        row_inflight = true;
-        if (ncand < a.cand_cap) { pend_id = node; pending = true; }
-      }
-#else
-      if (MODE != kExact && ncand < a.cand_cap) {  // (the previous staged node was consumed after its expansion)
-        stage_vec(a, s, node);
-        pend_id = node;
-        pending = true;
-      }
-#endif
-#endif
       if (ncand < a.cand_cap) ++ncand;
     };
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
-#ifdef BANG_TMA_ROWS
-      row_arrived();
-#endif
-      uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, true, &deg, pf);
-      sum_deg += deg; n_pass += n;
-#ifdef BANG_EAGER_EXACT
-      eager_consume();
-#endif
+      uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, true, pf);
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
       uint32_t parent = b.id, mark = have ? b.id : 0x01010101u;
@@ -1157,9 +1005,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       uint32_t pend_n = n, pend_nb = min(n, a.L), pend_below = 0, scan_from = 0;
       float pend_maxd = 0.0f;
       while (have || pend_n > 0) {
-#ifndef BANG_TMA_ROWS
         if (have) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
-#endif
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
           ws = merge_worklist(a, s, pend_n, pend_nb, pend_below, pend_maxd, ws, iter == 1, mark, &pos0);
           scan_from = min(scan_from, pos0);
@@ -1167,13 +1013,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
         n = 0;
-#ifdef BANG_TMA_ROWS
-        if (have) row_arrived();
-#endif
-        if (have) { n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, &deg, pf); sum_deg += deg; n_pass += n; }
-#ifdef BANG_EAGER_EXACT
-        eager_consume();
-#endif
+        if (have) n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, pf);
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
@@ -1194,12 +1034,8 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         pend_nb = n ? admit_count(b.below, n, ws, a.L) : 0u;
         if (iter == a.max_iter - 1) break;
       }
-#ifdef BANG_EAGER_EXACT
-      eager_consume();  // a node logged by the capped last iteration is never expanded, but it is a candidate
-      write_topk(a, s, q, tkn);
-#else
+      write_stats(a, s, q);
       rerank_and_write<T>(a, s, q, ncand);
-#endif
     } else {
       // ---- BANG_Inmemory / BANG_Exactdistance (A.2', A.2''): { expand(parent) ; merge ; first unvisited } ----
       // The first unvisited entry after the merge is decided before it: the closest new entry if it is
@@ -1207,14 +1043,11 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-#ifdef BANG_TMA_ROWS
-        row_arrived();
-#endif
-        const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, &deg, pf);
-        sum_deg += deg; n_pass += n;
-#ifdef BANG_EAGER_EXACT
-        eager_consume();
-#endif
+        const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, pf);
+        // Exactdistance: a hop whose neighbours are all filtered out ends the query — what the reference's fused
+        // kernel does when built for sm_100a (it scans the worklist up to a size it only sets when there are new
+        // neighbours, BANG_Exactdistance/parANN.cu:1593,1600,1671; pinned by tests/golden/ref_forks_golden.npz).
+        if (MODE == kExact && a.stop_on_empty_hop && !first && n == 0) break;
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
         const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
         pf.tick(PT_SCAN);
@@ -1230,16 +1063,15 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
           if (nb > 0 && (fu == kNone || b.d <= s.w_d[fu])) { have = true; from_new = true; parent = b.id; }
           else if (fu != kNone) { have = true; parent = s.w_id[fu]; }
         }
-        if (!have) break;  // nothing unvisited and nothing admitted: the merge would be a no-op
+        if (!have) {  // nothing unvisited and nothing admitted: the merge would be a no-op, except for a first hop that
+          if (first && nb > 0) ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, true, kNone, &pos0);  // found only the medoid
+          break;
+        }
         uint32_t scan_from = fu == kNone ? ws : fu;
         if (!from_new) { if (lane == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
         log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
         const bool capped = iter == a.max_iter - 1;
-#ifdef BANG_TMA_ROWS
-        if (MODE == kExact && !capped) my_nb = fetch_adj(a, parent, pol_stream);
-#else
         if (!capped) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
-#endif
         pf.tick(PT_DECIDE);
         if (nb > 0) {
           ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, first, from_new ? parent : kNone, &pos0);
@@ -1253,6 +1085,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         if (capped) break;
         ++iter;
       }
+      write_stats(a, s, q);
       if (MODE == kExact) {
         // top-k = head of the worklist (Exact parANN.cu:1273-1276)
         __syncwarp();
@@ -1261,12 +1094,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
           a.out_dists[(size_t)q * a.k + r] = r < ws ? s.w_d[r] : 3.402823466e+38f;
         }
       } else {
-#ifdef BANG_EAGER_EXACT
-        eager_consume();
-        write_topk(a, s, q, tkn);
-#else
         rerank_and_write<T>(a, s, q, ncand);
-#endif
         pf.tick(PT_RERANK);
       }
     }
@@ -1280,8 +1108,6 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, (MODE == kExact) ? 2 : (
         a.dump_n[q] = min(ncand, a.dump_stride);
       }
       if (a.st_hops) a.st_hops[q] = ncand;
-      if (a.st_sumdeg) a.st_sumdeg[q] = sum_deg;
-      if (a.st_npass) a.st_npass[q] = n_pass;
     }
     __syncwarp();
   }
@@ -1302,23 +1128,28 @@ __global__ void __launch_bounds__(32) pq_table_kernel(const SearchArgs a, float*
 // host-side launch geometry: how many query warps fit in one CTA / SM
 // ------------------------------------------------------------------------------------------------
 struct LaunchGeom { int warps_per_cta; int ctas_per_sm; size_t smem; };
+// the kernel variant (WPC) that runs `warps` query warps per CTA
+inline int wpc_variant(int mode, int warps) { return (mode == kExact || warps <= 16) ? 16 : 32; }
 template <typename T>
 inline LaunchGeom launch_geometry(int mode, uint32_t D, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap,
-                                  size_t smem_optin_per_block, size_t smem_per_sm, int max_warps_per_sm) {
-  const size_t shared = cta_shared_bytes(mode, D, n_chunks), per = warp_private_bytes<T>(mode, D, vec_units, L, cand_cap);
+                                  size_t smem_optin_per_block, size_t smem_per_sm, int max_warps_per_sm, bool piv_global = false) {
+  const size_t shared = cta_shared_bytes(mode, D, n_chunks, piv_global), per = warp_private_bytes<T>(mode, D, vec_units, L, cand_cap);
   LaunchGeom g{0, 0, 0};
   if (shared + per > smem_optin_per_block) return g;
   int w = (int)((smem_optin_per_block - shared) / per);
-  if (w > kMaxWarpsPerCta) w = kMaxWarpsPerCta;
+  const int cap = mode == kExact ? 16 : kMaxWarpsPerCta;
+  if (w > cap) w = cap;
   if (max_warps_per_sm > 0 && w > max_warps_per_sm) w = max_warps_per_sm;
   g.warps_per_cta = w;
   g.smem = shared + (size_t)w * per;
-  // several small CTAs per SM when the shared part is small (e.g. exact mode): bounded by smem and 64 warps/SM
-  int c = (int)(smem_per_sm / (g.smem + 1024));
-  if (c < 1) c = 1;
-  if (c * w > 64) c = 64 / w;
-  if (max_warps_per_sm > 0 && c * w > max_warps_per_sm) c = max_warps_per_sm / w;
-  if (c < 1) c = 1;
+  // Exactdistance (no CTA-shared table): several CTAs per SM, bounded by shared memory and the warp budget
+  int c = 1;
+  if (mode == kExact) {
+    c = (int)(smem_per_sm / (g.smem + 1024));
+    if (c > 2) c = 2;  // the kernel's launch bound
+    if (max_warps_per_sm > 0 && c * w > max_warps_per_sm) c = max_warps_per_sm / w;
+    if (c < 1) c = 1;
+  }
   g.ctas_per_sm = c;
   return g;
 }
