@@ -115,8 +115,10 @@ def find_medoid(base: torch.Tensor) -> int:
 
 
 def make_fixture_auto(prefix: str, n: int, d: int, dtype: str, nq: int, m: int | None, k_gt: int = 100, device="cpu",
-                      builder: str = "auto", L_build: int = 64, alpha: float = 1.2, seed: int = synth.BASE_SEED) -> dict:
-    """Like make_fixture, but everything (data, graph, PQ, ground truth) is produced on `device` when it is a GPU."""
+                      builder: str = "auto", L_build: int = 64, alpha: float = 1.2, seed: int = synth.BASE_SEED,
+                      n_gt_queries: int | None = None) -> dict:
+    """Like make_fixture, but everything (data, graph, PQ, ground truth) is produced on `device` when it is a GPU.
+    n_gt_queries: ground truth for the first n_gt_queries queries only (bench.py: one batch of the query file)."""
     import time
     dev = torch.device(device)
     use_gpu = dev.type == "cuda" and builder in ("auto", "gpu")
@@ -143,7 +145,7 @@ def make_fixture_auto(prefix: str, n: int, d: int, dtype: str, nq: int, m: int |
         codes = synth.encode_pq(base, piv, cen, offs).cpu().numpy()
     t["pq"] = time.time() - t0
     t0 = time.time()
-    gt_ids, gt_d = synth.brute_force_gt(base, queries, min(k_gt, n))
+    gt_ids, gt_d = synth.brute_force_gt(base, queries if n_gt_queries is None else queries[:n_gt_queries], min(k_gt, n))
     t["gt"] = time.time() - t0
     t0 = time.time()
     paths = formats.write_index(prefix, base.cpu().numpy(), deg, nbrs, medoid, piv, cen, offs, codes)

@@ -1,5 +1,5 @@
 // search_inst.cuh — the fused search kernel is instantiated once per element type, each in its own translation unit
-// (search_inst_u8.cu / _i8.cu / _f32.cu: 13 kernels apiece, compiled in parallel by build.py); the host code picks
+// (search_inst_u8.cu / _i8.cu / _f32.cu: 19 kernels apiece, compiled in parallel by build.py); the host code picks
 // an instantiation through these lookups.
 #pragma once
 #include "search_kernel.cuh"
@@ -8,7 +8,7 @@ namespace bang {
 typedef void (*search_fn_t)(const SearchArgs);
 typedef void (*table_fn_t)(const SearchArgs, float*);
 
-// mode: 0 Base / 1 Inmemory / 2 Exactdistance; cs: uniform PQ chunk size 4, 3 or 0 (general); wpc: 16 or 32 (wpc_variant)
+// mode: 0 Base / 1 Inmemory / 2 Exactdistance; cs: uniform PQ chunk size 4, 3 or 0 (general); wpc: 16, 24 or 32 (wpc_variant)
 search_fn_t search_kernel_u8(int mode, uint32_t cs, int wpc);
 search_fn_t search_kernel_i8(int mode, uint32_t cs, int wpc);
 search_fn_t search_kernel_f32(int mode, uint32_t cs, int wpc);
@@ -23,7 +23,7 @@ static search_fn_t inst_mode(int mode) {
 }
 template <typename T, int CS>
 static search_fn_t inst_wpc(int mode, int wpc) {
-  return wpc <= 16 ? inst_mode<T, CS, 16>(mode) : inst_mode<T, CS, 32>(mode);
+  return wpc <= 16 ? inst_mode<T, CS, 16>(mode) : (wpc <= 24 ? inst_mode<T, CS, 24>(mode) : inst_mode<T, CS, 32>(mode));
 }
 template <typename T>
 static search_fn_t inst_lookup(int mode, uint32_t cs, int wpc) {

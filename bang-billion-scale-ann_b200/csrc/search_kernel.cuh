@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(32) pq_table_kernel(const SearchArgs a, float*
 // ------------------------------------------------------------------------------------------------
 struct LaunchGeom { int warps_per_cta; int ctas_per_sm; size_t smem; };
 // the kernel variant (WPC) that runs `warps` query warps per CTA
-inline int wpc_variant(int mode, int warps) { return (mode == kExact || warps <= 16) ? 16 : 32; }
+inline int wpc_variant(int mode, int warps) { return (mode == kExact || warps <= 16) ? 16 : (warps <= 24 ? 24 : 32); }
 template <typename T>
 inline LaunchGeom launch_geometry(int mode, uint32_t D, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap,
                                   size_t smem_optin_per_block, size_t smem_per_sm, int max_warps_per_sm, bool piv_global = false) {

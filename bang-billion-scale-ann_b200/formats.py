@@ -155,11 +155,31 @@ def pack_disk_bin(vectors: np.ndarray, degrees: np.ndarray, nbrs: np.ndarray) ->
 
 
 def write_disk_bin(path: str, vectors, degrees, nbrs) -> None:
+    """Packs and writes in 256 MB pieces; large files (10^8 points: 64 GB) use several threads, each writing its pieces
+    at their offsets (numpy's copies release the GIL)."""
     N = vectors.shape[0]
-    step = max(1, (256 << 20) // max(1, entry_len(vectors.shape[1], dtype_name(vectors), nbrs.shape[1])))
+    el = entry_len(vectors.shape[1], dtype_name(vectors), nbrs.shape[1])
+    step = max(1, (256 << 20) // max(1, el))
+    starts = list(range(0, N, step))
     with open(path, "wb") as f:
-        for s in range(0, N, step):
-            f.write(pack_disk_bin(vectors[s:s + step], degrees[s:s + step], nbrs[s:s + step]).tobytes())
+        f.truncate(N * el)
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        def piece(s):
+            buf = memoryview(pack_disk_bin(vectors[s:s + step], degrees[s:s + step], nbrs[s:s + step]).reshape(-1))
+            off = s * el
+            while len(buf):
+                w = os.pwrite(fd, buf[:1 << 30], off)
+                buf, off = buf[w:], off + w
+        if len(starts) <= 4:
+            for s in starts:
+                piece(s)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+                list(ex.map(piece, starts))
+    finally:
+        os.close(fd)
 
 
 def write_disk_metadata(path: str, meta: GraphMeta) -> None:

@@ -2,28 +2,36 @@
 """bench.py — QPS of the batched greedy Vamana search at recall@10 >= 0.90 / 0.95 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference ...                     # host-core baseline (oracle port, all cores)
+    python bench.py --impl reference ...                     # the reference's search logic on the host cores
+    python bench.py --prepare --workload W                   # build + cache the index files and the operating points
 
-A "step" is one pass of the hot path over one batch of Q = 10 000 queries.  Default workload = BASELINE.json
-configs[1]: SIFT1M-shape synthetic (N = 10^6, D = 128, uint8, R = 64, PQ 32 B/vector), BANG_Inmemory
-semantics, k = 10.  The index (data, Vamana graph, PQ, ground truth) is generated on the box by the
-committed builder and written in the reference's file formats; the search loads those files through
-bang_load.  The worklist length L is the smallest of a sweep reaching the recall target (found before the
-timed region, as the reference's driver sweeps L, test_driver.cpp:388-420).
+A "step" is one pass of the hot path over one batch of Q = 10 000 queries.  Default workload = the largest
+single-GPU configuration of BASELINE.json, C4: DEEP100M-shape synthetic (N = 10^8, D = 96 fp32, R = 64, PQ 32 B per
+vector), BANG_Inmemory semantics, k = 10, index replicated per GPU.  At N = 1 the line also carries C2 (SIFT1M
+shape) and C3 (GIST1M shape, Exactdistance) under "other_configs", each with its own roofline.  `--workload sift1b`
+/ `sift256m` run the sharded configuration C5 (graph rows sharded over the GPUs' HBM, NVLink P2P fetch) under torchrun.
 
-JSON line (one, from rank 0): see the contract in the task statement; `value` = whole-job QPS at
-recall@10 >= 0.90 with queries already resident in HBM (device-side CUDA events, max over ranks);
-`e2e` = the same through the host-facing bang_query call (host query buffer in, host ids/dists out);
-`at_recall_95` repeats both at the >= 0.95 operating point.
+The index (data, Vamana graph, PQ, ground truth) is generated on the box by the committed GPU builder, written in the
+reference's file formats into a cache directory (/dev/shm when it is large enough, else /tmp) and loaded through
+bang_load.  The worklist lengths L for recall >= 0.90 / 0.95 come from one sweep over the full first batch (as the
+reference's driver sweeps L, test_driver.cpp:388-420); they are cached next to the files, so the reference arm runs
+at the SAME operating point.  The reference arm does not load this repo's CUDA library: when the cache is missing it
+runs `bench.py --prepare` in a child process and then only reads the files.
+
+JSON line (one, from rank 0): `value` = whole-job QPS at recall@10 >= 0.90 with queries already resident in HBM
+(CUDA events on the launching stream, max over ranks); `e2e` = the same through the host-facing bang_query call
+(pinned host query buffer in, host ids/dists out); `at_recall_95` repeats both at the >= 0.95 operating point;
+`strong_scaling` = the same 10 000 queries split over the ranks.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
+import shutil
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -33,18 +41,32 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: dict(n, d, dtype, m, q, mode)
     "sift10k": dict(n=10_000, d=128, dtype="uint8", m=32, q=100, mode="inmemory", label="C1 SIFT10K-shape"),
     "sift1m": dict(n=1_000_000, d=128, dtype="uint8", m=32, q=10_000, mode="inmemory", label="C2 SIFT1M-shape"),
     "gist1m": dict(n=1_000_000, d=960, dtype="float", m=None, q=10_000, mode="exact", label="C3 GIST1M-shape"),
     "deep100m": dict(n=100_000_000, d=96, dtype="float", m=32, q=10_000, mode="inmemory", label="C4 DEEP100M-shape"),
+    # sharded (C5): no files, built on the GPUs under torchrun
+    "sift256m": dict(n=256_000_000, d=128, dtype="uint8", m=32, q=10_000, mode="inmemory", label="C5 SIFT1B-shape at 256 M points", sharded=True),
+    "sift1b": dict(n=1_000_000_000, d=128, dtype="uint8", m=32, q=10_000, mode="inmemory", label="C5 SIFT1B-shape", sharded=True),
 }
+DEFAULT_WORKLOAD = "deep100m"
 K = 10
-L_SWEEP = (10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 56, 64, 80, 96, 112, 128, 152, 176, 200, 256, 320, 400, 512)
+MAX_WORLD = 8  # query files hold one batch per GPU of the box
+L_SWEEP = (10, 12, 14, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 80, 96, 112, 128, 152, 176, 200, 256, 320, 400, 512)
+METRIC = "QPS at recall@10 >= 0.90 (batched greedy Vamana search)"
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def esize(wl):
+    return 4 if wl["dtype"] == "float" else 1
+
+
+def label(wl, Qtot):
+    return (f"{wl['label']}: N={wl['n']} D={wl['d']} {wl['dtype']} R=64 " + (f"PQ m={wl['m']}" if wl["m"] else "no PQ")
+            + f", Q={Qtot}, k={K}, mode={wl['mode']}")
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -94,51 +116,78 @@ class ClockSampler:
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        # the sampler runs across load, warm-up and the timed steps: the clock under load is the upper half of the samples
+        hot = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(hot)) if hot else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def kernel_source_hash() -> str:
+    h = hashlib.sha256()
+    for f in ("search_kernel.cuh", "bang_b200.cu"):
+        with open(os.path.join(ROOT, "bang-billion-scale-ann_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(workload: str, mode: str, L: int, q: int):
-    """DRAM bytes (read + write) of one launch of the search kernel from the committed ncu capture, if that
-    capture was taken on this very workload / mode / L / batch; else None (B200 bench contract: traffic or null)."""
+    """DRAM bytes (read + write) of one launch of the search kernel from a committed `ncu` capture — only when that
+    capture was taken on this very workload / mode / L / batch with the kernel source as it is now; else None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1e_traffic.json")) as f:
-            t = json.load(f)
-        if (t["workload"], t["mode"], t["L"], t["queries"]) == (workload, mode, L, q):
-            return t["dram_bytes_read"] + t["dram_bytes_write"]
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            for t in json.load(f):
+                if (t["workload"], t["mode"], t["L"], t["queries"], t["kernel_source_hash"]) == (workload, mode, L, q, kernel_source_hash()):
+                    return t["dram_bytes_read"] + t["dram_bytes_write"]
     except Exception:
         pass
     return None
 
 
 # ----------------------------------------------------------------------------------------------------
-# index generation
+# index cache: files in the reference's formats + meta.json (operating points)
 # ----------------------------------------------------------------------------------------------------
-def make_index(wl: dict, workdir: str, device, builder: str, rank: int, world: int):
-    """Rank 0 generates the dataset + index files; the other ranks wait for them (same box)."""
-    import bang_b200  # noqa: F401
-    from bang_b200 import builder as B
-    nq = wl["q"] * max(1, world)  # weak scaling: every rank searches its own batch of wl["q"] queries
-    prefix = os.path.join(workdir, f"{wl['dtype']}_{wl['n']}_{wl['d']}_q{nq}")
-    done = prefix + ".done"
-    if rank == 0 and not os.path.exists(done):
-        t0 = time.time()
-        info = B.make_fixture_auto(prefix, wl["n"], wl["d"], wl["dtype"], nq, wl["m"], k_gt=100, device=device,
-                                   builder=builder)
-        log(f"[bench] index built in {time.time() - t0:.1f}s ({info})")
-        with open(done, "w") as f:
-            f.write("ok")
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    return prefix
+def index_bytes(wl) -> int:
+    el = wl["d"] * esize(wl) + 4 + 256
+    return int(wl["n"] * (el + (wl["m"] or 0)) * 1.02) + (64 << 20)
 
 
-def pick_L(search, queries, gt_ids, gt_d, targets=(90.0, 95.0)):
-    """Smallest L of the sweep reaching each recall target (outside the timed region)."""
+def prefix_name(wl) -> str:
+    return f"{wl['dtype']}_{wl['n']}_{wl['d']}_m{wl['m'] or 0}_q{wl['q']}"
+
+
+def cache_dirs(args):
+    if args.workdir:
+        return [args.workdir]
+    out = []
+    if os.environ.get("BANG_B200_BENCH_DIR"):
+        out.append(os.environ["BANG_B200_BENCH_DIR"])
+    return out + ["/dev/shm/bang_b200_bench", "/tmp/bang_b200_bench"]
+
+
+def find_cached(wl, args):
+    for d in cache_dirs(args):
+        p = os.path.join(d, prefix_name(wl))
+        if os.path.exists(p + ".meta.json"):
+            return p
+    return None
+
+
+def pick_cache_dir(wl, args) -> str:
+    need = index_bytes(wl)
+    for d in cache_dirs(args):
+        try:
+            os.makedirs(d, exist_ok=True)
+            if shutil.disk_usage(d).free > need:
+                return d
+        except OSError:
+            continue
+    raise SystemExit(f"bench.py: no cache directory with {need >> 30} GiB free among {cache_dirs(args)}")
+
+
+def sweep_L(search, queries, gt_ids, gt_d, targets=(90.0, 95.0)):
+    """Smallest L of the sweep reaching each recall target, on the full batch (outside any timed region)."""
     from bang_b200 import recall
-    found = {}
-    curve = []
+    found, curve = {}, []
     Q = len(queries)
     for L in L_SWEEP:
         if L < K:
@@ -158,19 +207,63 @@ def pick_L(search, queries, gt_ids, gt_d, targets=(90.0, 95.0)):
     return found, curve
 
 
+def prepare(wl, args) -> str:
+    """Builds the index with the GPU builder, writes the reference's files, finds L90 / L95 with this repo's search and
+    caches everything.  Runs in the b200 arm's own process, or as `bench.py --prepare` (a child of the reference arm)."""
+    import torch
+    import bang_b200  # noqa: F401
+    from bang_b200 import api, builder as B, formats
+    got = find_cached(wl, args)
+    if got:
+        return got
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --prepare: the index builder needs a CUDA device")
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    prefix = os.path.join(pick_cache_dir(wl, args), prefix_name(wl))
+    t0 = time.time()
+    info = B.make_fixture_auto(prefix, wl["n"], wl["d"], wl["dtype"], wl["q"] * MAX_WORLD, wl["m"], k_gt=100, device=device,
+                               builder=args.builder, n_gt_queries=wl["q"])
+    torch.cuda.empty_cache()
+    log(f"[bench] index built in {time.time() - t0:.1f}s ({info})")
+    paths = formats.IndexPaths(prefix)
+    queries = formats.read_bin(paths.query, api.NP[wl["dtype"]])[: wl["q"]]
+    gt_ids, gt_d = formats.read_truthset(paths.truth)
+    s = api.BANGSearch(wl["dtype"], wl["mode"], device=device.index)
+    t1 = time.time()
+    if not s.bang_load(prefix):
+        raise SystemExit("bang_load failed: " + s.last_error)
+    t_load = time.time() - t1
+    found, curve = sweep_L(s, queries, gt_ids, gt_d)
+    s.bang_unload()
+    if 90.0 not in found or 95.0 not in found:
+        raise SystemExit(f"recall targets not reached in the L sweep: {curve}")
+    meta = {"L90": found[90.0][0], "L95": found[95.0][0], "recall_curve": curve, "build": info, "bang_load_s": round(t_load, 1),
+            "prepare_s": round(time.time() - t0, 1), "queries_in_file": wl["q"] * MAX_WORLD, "gt_queries": wl["q"]}
+    with open(prefix + ".meta.json", "w") as f:
+        json.dump(meta, f)
+    log(f"[bench] prepared {prefix}: {meta}")
+    return prefix
+
+
+def read_meta(prefix):
+    with open(prefix + ".meta.json") as f:
+        return json.load(f)
+
+
 # ----------------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------------
 def time_config(search, queries_np, L, steps, warmup, device, world):
-    """Returns dict with device-resident QPS, e2e QPS, stats for one worklist length."""
+    """Device-resident and end-to-end timings of one worklist length on this rank's batch."""
     import torch
-    from bang_b200 import api
     Q = len(queries_np)
     search.bang_set_searchparams(K, L)
     search.bang_alloc(Q)
     search.bang_init(Q)
     stream = torch.cuda.current_stream(device)
-    d_q = torch.from_numpy(queries_np).to(device)
+    h_q = torch.from_numpy(queries_np).pin_memory()  # e2e: the step's inputs come from pinned host memory
+    q_host = h_q.numpy()
+    d_q = h_q.to(device)
     d_ids = torch.empty((Q, K), dtype=torch.int64, device=device)
     d_d = torch.empty((Q, K), dtype=torch.float32, device=device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
@@ -187,22 +280,20 @@ def time_config(search, queries_np, L, steps, warmup, device, world):
         search.query_device(d_q.data_ptr(), Q, d_ids.data_ptr(), d_d.data_ptr(), stream.cuda_stream)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
-    t_wall0 = time.perf_counter()
     for s in range(steps):
-        flush.zero_()  # L2 flush between timed iterations (the index itself, 384 MB + 32 MB, also exceeds L2)
+        flush.zero_()  # L2 flush between timed iterations (the index itself also exceeds L2)
         ev[s][0].record(stream)
         search.query_device(d_q.data_ptr(), Q, d_ids.data_ptr(), d_d.data_ptr(), stream.cuda_stream)
         ev[s][1].record(stream)
     barrier()
-    t_wall = time.perf_counter() - t_wall0
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     stats = search.last_stats(Q)
     ids_dev = d_ids.cpu().numpy().astype(np.uint64)
 
-    # ---- end to end: host query buffer -> bang_query -> host ids/dists (H2D + D2H inside) ----
+    # ---- end to end: pinned host query buffer -> bang_query -> host ids/dists (H2D + D2H inside) ----
     for _ in range(max(1, warmup // 2)):
         search.bang_init(Q)
-        search.bang_query(queries_np)
+        search.bang_query(q_host)
     e2e_ms = []
     barrier()
     for s in range(steps):
@@ -210,26 +301,26 @@ def time_config(search, queries_np, L, steps, warmup, device, world):
         torch.cuda.synchronize(device)
         search.bang_init(Q)
         t0 = time.perf_counter()
-        ids_host, _ = search.bang_query(queries_np)
+        ids_host, _ = search.bang_query(q_host)
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     tm = search.last_timing()
     assert np.array_equal(ids_host, ids_dev), "device-resident and host paths disagree"
     search.bang_free()
-    return dict(kern_ms=kern_ms, e2e_ms=e2e_ms, stats=stats, ids=ids_host, timing=tm, wall_s=t_wall)
+    del flush
+    return dict(kern_ms=kern_ms, e2e_ms=e2e_ms, stats=stats, ids=ids_host, timing=tm)
 
 
 def cpu_baseline_sample(prefix, wl, queries, L, target_s=12.0):
     """Oracle port timed on the host cores on a bounded sample of the same workload (rank 0, N=1 only)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    ox = O.OracleIndex.from_files(prefix, with_pq=wl["mode"] != "exact")
+    ox = O.OracleIndex.from_files(prefix, with_pq=wl["mode"] != "exact", mmap=True)
     mode = {"base": O.MODE_BASE, "inmemory": O.MODE_INMEMORY, "exact": O.MODE_EXACT}[wl["mode"]]
     cores = os.cpu_count() or 1
     n = min(len(queries), max(64, 4 * cores))
     t0 = time.perf_counter()
-    ox.search(queries[:n], K, L, mode=mode, nthreads=cores)
+    ox.search(queries[:n], K, L, mode=mode, nthreads=cores)   # (also pages the touched part of the index in)
     dt = time.perf_counter() - t0
-    # scale the sample to ~target_s of CPU work
     n2 = int(min(len(queries), max(n, n * target_s / max(dt, 1e-3))))
     t0 = time.perf_counter()
     ox.search(queries[:n2], K, L, mode=mode, nthreads=cores)
@@ -238,18 +329,19 @@ def cpu_baseline_sample(prefix, wl, queries, L, target_s=12.0):
                 sample=f"{n2} of {len(queries)} queries at L={L}, oracle/bang_oracle.c with OpenMP over queries")
 
 
-def reference_cuda_run(prefix, wl, paths, Q, L, gt_ids, gt_d):
-    """The UNMODIFIED reference (BANG_Base built from /root/reference into oracle/_ref, sm_100a) on this GPU over the
-    same index files: its own BANGSearch<T> API through oracle/ref_driver.cpp, 4 runs, first discarded (the
-    authors' protocol, BANG_Inmemory/parANN.h:30-31).  Comparison only; PQ modes only."""
-    from bang_b200 import recall
+def reference_cuda_run(prefix, wl, paths, queries, L, gt_ids, gt_d, device_index):
+    """The UNMODIFIED reference (BANG_Base built from /root/reference into oracle/_ref, sm_100a) on this GPU over the same
+    index files: its own BANGSearch<T> API through oracle/ref_driver.cpp, 4 runs, first discarded (the authors' protocol,
+    BANG_Inmemory/parANN.h:30-31) — next to this repo's library in the SAME storage mode (Base) at the same L: share of
+    queries with identical top-k ids and the recall difference.  Comparison only; PQ modes only."""
+    from bang_b200 import api, recall
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     if not os.path.exists(exe) or wl["mode"] == "exact":
         return None
+    Q = len(queries)
     out = os.path.join(os.path.dirname(prefix), "ref_ids.bin")
-    dt = {"uint8": "uint8", "int8": "int8", "float": "float"}[wl["dtype"]]
     try:
-        r = subprocess.run([exe, prefix, paths.query, str(Q), str(K), str(L), dt, out, "4"], capture_output=True, text=True,
+        r = subprocess.run([exe, prefix, paths.query, str(Q), str(K), str(L), wl["dtype"], out, "4"], capture_output=True, text=True,
                            timeout=900)
     except Exception as e:  # noqa: BLE001
         return {"error": str(e)[:200]}
@@ -260,8 +352,66 @@ def reference_cuda_run(prefix, wl, paths, Q, L, gt_ids, gt_d):
     rec = recall.calculate_recall(gt_ids[:Q], gt_d[:Q], ids, K)
     use = ms[1:] if len(ms) > 1 else ms
     gm = float(np.exp(np.mean(np.log(use))))
-    return {"qps": Q / (gm * 1e-3), "ms": gm, "runs_ms": ms, "L": L, "recall_at_10": round(rec, 2),
+    s = api.BANGSearch(wl["dtype"], "base", device=device_index)
+    same = None
+    if s.bang_load(prefix):
+        s.bang_set_searchparams(K, L)
+        s.bang_alloc(Q); s.bang_init(Q)
+        mine, _ = s.bang_query(queries)
+        s.bang_free(); s.bang_unload()
+        same = {"identical_topk_ids_pct": round(float((mine == ids).all(1).mean()) * 100, 2),
+                "same_id_sets_pct": round(float((np.sort(mine, 1) == np.sort(ids, 1)).all(1).mean()) * 100, 2),
+                "recall_at_10_this_repo_base_mode": round(recall.calculate_recall(gt_ids[:Q], gt_d[:Q], mine, K), 2)}
+    return {"qps": Q / (gm * 1e-3), "ms": gm, "runs_ms": ms, "L": L, "recall_at_10": round(rec, 2), "same_mode_agreement": same,
             "what": "unmodified BANG_Base (oracle/_ref/libbang.so, nvcc -arch sm_100a) via its BANGSearch<T> API, wall clock around bang_query"}
+
+
+def measure(wl, prefix, meta, args, device, rank, world, local, per_rank_q, points=(90.0, 95.0)):
+    """Loads the cached index on this rank and times the operating points.  Returns (dict per recall target, search info)."""
+    import bang_b200  # noqa: F401
+    from bang_b200 import api, formats, recall, sharding
+    paths = formats.IndexPaths(prefix)
+    allq = formats.read_bin(paths.query, api.NP[wl["dtype"]])
+    gt_ids, gt_d = formats.read_truthset(paths.truth)
+    lo = rank * per_rank_q
+    my_q = np.ascontiguousarray(allq[lo:lo + per_rank_q])
+    search = api.BANGSearch(wl["dtype"], wl["mode"], device=local)
+    t0 = time.time()
+    if not search.bang_load(prefix):
+        raise SystemExit("bang_load failed: " + search.last_error)
+    log(f"[bench r{rank}] bang_load {time.time() - t0:.1f}s, index {search.info().device_bytes / 2**20:.0f} MiB in HBM")
+    search.set_dists_layout(api.DISTS_QUERY_MAJOR)
+    out = {}
+    for tgt in points:
+        L = {90.0: args.L or meta["L90"], 95.0: args.L95 or args.L or meta["L95"]}[tgt]
+        r = time_config(search, my_q, L, args.steps, args.warmup, device, world)
+        kern = sharding.max_over_ranks(r["kern_ms"], device=device)
+        e2e = sharding.max_over_ranks(r["e2e_ms"], device=device)
+        ids_all = sharding.gather_rows(r["ids"])
+        stats_all = {k_: sharding.gather_rows(v) for k_, v in r["stats"].items()}
+        n_gt = min(len(gt_ids), per_rank_q)   # the ground truth covers the first batch (rank 0's)
+        rec = recall.calculate_recall(gt_ids[:n_gt], gt_d[:n_gt], ids_all[:n_gt], K)
+        bq = api.algorithmic_bytes(stats_all, wl["mode"], wl["d"], esize(wl), wl["m"] or 0, K)
+        my_b = float(api.algorithmic_bytes(r["stats"], wl["mode"], wl["d"], esize(wl), wl["m"] or 0, K).sum())
+        ms = float(np.mean(kern))
+        out[tgt] = dict(L=L, recall=rec, ms=ms, qps=len(ids_all) / (ms * 1e-3), e2e_ms=float(np.mean(e2e)),
+                        e2e_qps=len(ids_all) / (np.mean(e2e) * 1e-3), bytes_per_query=float(bq.mean()),
+                        hops=float(stats_all["hops"].mean()), n_cand=float(stats_all["n_cand"].mean()), timing=r["timing"],
+                        my_bytes=my_b, my_ms=float(np.mean(r["kern_ms"])), queries=len(ids_all))
+    info = search.info()
+    search.bang_unload()
+    del search
+    return out, info, (allq, gt_ids, gt_d, paths)
+
+
+def roofline_of(p, wl, workload_name, peak_gbs, peak_src):
+    ach = p["my_bytes"] / (p["my_ms"] * 1e-3) / 1e9  # rank-0 kernel: algorithmic bytes per launch / its duration
+    tm = p["timing"]
+    return {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+            "traffic": ncu_traffic(workload_name, wl["mode"], p["L"], wl["q"]),
+            "kernel": "bang_search_kernel (fused traversal, 1 launch per step)", "bytes_per_query": p["bytes_per_query"],
+            "hops_per_query": p["hops"], "candidates_per_query": p["n_cand"], "peak_source": peak_src,
+            "grid": tm.grid, "block": tm.block, "smem_bytes": tm.smem_bytes, "ctas_per_sm": tm.ctas_per_sm}
 
 
 def run_b200(args):
@@ -276,79 +426,37 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    import bang_b200  # noqa: F401
-    from bang_b200 import api, formats, recall
+    wl = workload(args)
+    if wl.get("sharded"):
+        return run_sharded(args, wl, device, rank, world, local)
 
-    wl = dict(WORKLOADS[args.workload])
-    if args.n:
-        wl["n"] = args.n
-    if args.q:
-        wl["q"] = args.q
-    workdir = args.workdir or os.path.join(tempfile.gettempdir(), "bang_b200_bench")
-    os.makedirs(workdir, exist_ok=True)
-    prefix = make_index(wl, workdir, device, args.builder, rank, world)
-    paths = formats.IndexPaths(prefix)
-    queries = formats.read_bin(paths.query, api.NP[wl["dtype"]])[: wl["q"] * world]
-    gt_ids, gt_d = formats.read_truthset(paths.truth)
+    def ensure(w):
+        p = None
+        if rank == 0:
+            p = prepare(w, args)
+        if world > 1:
+            import torch.distributed as dist
+            box = [p]
+            dist.broadcast_object_list(box, src=0)
+            p = box[0]
+        return p
 
-    # replicated index; every rank searches its own batch of wl["q"] queries (weak scaling), no collective on
-    # the data path
-    per = wl["q"]
-    lo, hi = rank * per, (rank + 1) * per
-    my_q = np.ascontiguousarray(queries[lo:hi])
-
-    search = api.BANGSearch(wl["dtype"], wl["mode"], device=local)
-    t0 = time.time()
-    if not search.bang_load(prefix):
-        raise SystemExit("bang_load failed: " + search.last_error)
-    log(f"[bench r{rank}] bang_load {time.time() - t0:.1f}s, index {search.info().device_bytes / 2**20:.0f} MiB in HBM")
-    search.set_dists_layout(api.DISTS_QUERY_MAJOR)
-
-    if args.L:
-        found = {90.0: (args.L, float("nan")), 95.0: (args.L95 or args.L, float("nan"))}
-        curve = []
-    else:
-        found, curve = pick_L(search, queries[:per], gt_ids[:per], gt_d[:per])  # every rank: same deterministic sweep on batch 0
-        if 90.0 not in found or 95.0 not in found:
-            raise SystemExit(f"recall targets not reached in the L sweep: {curve}")
+    prefix = ensure(wl)
+    meta = read_meta(prefix)
     if rank == 0:
-        log(f"[bench] recall curve {curve}; operating points {found}")
-
+        log(f"[bench] {prefix}: L90 {meta['L90']} L95 {meta['L95']} curve {meta['recall_curve']}")
     sampler = ClockSampler(local)
     sampler.start()
-    res = {}
-    for tgt in (90.0, 95.0):
-        L = found[tgt][0]
-        res[tgt] = time_config(search, my_q, L, args.steps, args.warmup, device, world)
+    strong = args.scaling == "strong"
+    per = wl["q"] // world if strong else wl["q"]
+    out, info, (allq, gt_ids, gt_d, paths) = measure(wl, prefix, meta, args, device, rank, world, local, per)
+    other_mode = None
+    if world > 1:   # the other scaling mode at the 0.90 point, for the record
+        om, _, _ = measure(wl, prefix, meta, args, device, rank, world, local, wl["q"] if strong else wl["q"] // world, points=(90.0,))
+        other_mode = om[90.0]
     clocks = sampler.stop()
-
-    # gather results: ids for the recall check, timings for max-over-ranks
-    from bang_b200 import sharding
-
-    def allmax(xs):
-        return sharding.max_over_ranks(xs, device=device)
-
-    gather_np = sharding.gather_rows
-
-    out = {}
-    for tgt in (90.0, 95.0):
-        r = res[tgt]
-        kern = allmax(r["kern_ms"])
-        e2e = allmax(r["e2e_ms"])
-        ids_all = gather_np(r["ids"])
-        stats_all = {k_: gather_np(v) for k_, v in r["stats"].items()}
-        rec = recall.calculate_recall(gt_ids[: len(ids_all)], gt_d[: len(ids_all)], ids_all, K)
-        esz = 4 if wl["dtype"] == "float" else 1
-        bq = api.algorithmic_bytes(stats_all, wl["mode"], wl["d"], esz, wl["m"] or 0, K)
-        ms = float(np.mean(kern))
-        out[tgt] = dict(L=found[tgt][0], recall=rec, ms=ms, qps=len(ids_all) / (ms * 1e-3),
-                        e2e_ms=float(np.mean(e2e)), e2e_qps=len(ids_all) / (np.mean(e2e) * 1e-3),
-                        bytes_per_query=float(bq.mean()), bytes_total=float(bq.sum()),
-                        hops=float(stats_all["hops"].mean()), n_cand=float(stats_all["n_cand"].mean()),
-                        timing=r["timing"], my_bytes=float(api.algorithmic_bytes(r["stats"], wl["mode"], wl["d"], esz, wl["m"] or 0, K).sum()),
-                        my_ms=float(np.mean(r["kern_ms"])))
-
     if rank != 0:
+        extra_ranks_done(world)
         return
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -357,47 +465,173 @@ def run_b200(args):
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     p90, p95 = out[90.0], out[95.0]
-    ach = p90["my_bytes"] / (p90["my_ms"] * 1e-3) / 1e9  # rank-0 kernel: algorithmic bytes per launch / its duration
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_sample(prefix, wl, queries, p90["L"])
-    tm = p90["timing"]
-    Qtot = len(queries)
-    esz = 4 if wl["dtype"] == "float" else 1
-    info = search.info()
+    Qtot = p90["queries"]
     line = {
-        "metric": "QPS at recall@10 >= 0.90 (batched greedy Vamana search)",
-        "value": p90["qps"], "unit": "QPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": p90["ms"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8 codes / fp32 ADC sums" if wl["mode"] != "exact" else "fp32",
-        "data": "synthetic clustered (Gaussian mixture), index built on the box by the committed builder",
-        "config": {"workload": f"{wl['label']}: N={wl['n']} D={wl['d']} {wl['dtype']} R=64 "
-                               + (f"PQ m={wl['m']}" if wl["m"] else "no PQ") + f", Q={Qtot}, k={K}, mode={wl['mode']}",
-                   "L_at_recall_90": p90["L"], "recall_at_10": round(p90["recall"], 2),
-                   "parallelism": f"index replicated on {world} GPU(s), one batch of {wl['q']} queries per GPU, no collective",
+        "metric": METRIC, "value": p90["qps"], "unit": "QPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": p90["ms"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u8 codes / fp32 ADC sums" if wl["mode"] != "exact" else "fp32",
+        "data": "synthetic clustered (Gaussian mixture), index built on the box by the committed GPU builder",
+        "config": {"workload": label(wl, Qtot), "L_at_recall_90": p90["L"], "recall_at_10": round(p90["recall"], 2),
+                   "parallelism": f"index replicated on {world} GPU(s), " + (f"one batch of {wl['q']} queries split over the GPUs" if strong
+                                                                              else f"one batch of {wl['q']} queries per GPU") + ", no collective",
                    "l2": "256 MiB buffer written between timed iterations; index (rows+codes) larger than L2",
-                   "builder": args.builder},
+                   "index_in_hbm_mib": int(info.device_bytes) >> 20, "kernel_source_hash": kernel_source_hash(), "builder": args.builder},
         "e2e": {"value": p90["e2e_qps"], "unit": "QPS", "ms_per_step": p90["e2e_ms"],
-                "h2d_bytes_per_step": int(Qtot * wl["d"] * esz), "d2h_bytes_per_step": int(Qtot * K * 12)},
+                "h2d_bytes_per_step": int(Qtot * wl["d"] * esize(wl)), "d2h_bytes_per_step": int(Qtot * K * 12)},
         "at_recall_95": {"L": p95["L"], "recall_at_10": round(p95["recall"], 2), "value": p95["qps"], "ms_per_step": p95["ms"],
                          "e2e": p95["e2e_qps"], "bytes_per_query": p95["bytes_per_query"]},
         "gpu_launches": args.steps * 1,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                     "traffic": ncu_traffic(args.workload, wl["mode"], p90["L"], wl["q"]),
-                     "kernel": "bang_search_kernel (fused traversal, 1 launch per step)",
-                     "bytes_per_query": p90["bytes_per_query"], "hops_per_query": p90["hops"],
-                     "candidates_per_query": p90["n_cand"], "peak_source": peak_src,
-                     "grid": tm.grid, "block": tm.block, "smem_bytes": tm.smem_bytes, "ctas_per_sm": tm.ctas_per_sm},
+        "roofline": roofline_of(p90, wl, args.workload, peak_gbs, peak_src),
         "clocks": clocks,
     }
-    if cpu:
-        line["cpu_baseline"] = cpu
-    if world == 1 and not args.no_ref_cuda:
-        search.bang_unload()
-        ref = reference_cuda_run(prefix, wl, paths, wl["q"], p90["L"], gt_ids, gt_d)
+    if other_mode:
+        line["strong_scaling" if not strong else "weak_scaling"] = {
+            "value": other_mode["qps"], "unit": "QPS", "ms_per_step": other_mode["ms"], "queries_total": other_mode["queries"],
+            "e2e": other_mode["e2e_qps"], "recall_at_10": round(other_mode["recall"], 2)}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(prefix, wl, allq[: wl["q"]], p90["L"])
+    if world == 1 and args.ref_cuda:
+        ref = reference_cuda_run(prefix, wl, paths, allq[: wl["q"]], p90["L"], gt_ids, gt_d, local)
         if ref:
             line["reference_cuda_b200"] = ref
+    if world == 1 and not args.no_extra and args.workload == DEFAULT_WORKLOAD:
+        line["other_configs"] = {}
+        for name in ("sift1m", "gist1m"):
+            try:
+                w2 = dict(WORKLOADS[name])
+                pf2 = prepare(w2, args)
+                m2 = read_meta(pf2)
+                a2 = argparse.Namespace(**{**vars(args), "L": 0, "L95": 0})
+                o2, i2, (q2, g2, gd2, paths2) = measure(w2, pf2, m2, a2, device, 0, 1, local, w2["q"])
+                e = {"workload": label(w2, w2["q"]), "L_at_recall_90": o2[90.0]["L"], "recall_at_10": round(o2[90.0]["recall"], 2),
+                     "value": o2[90.0]["qps"], "ms_per_step": o2[90.0]["ms"], "e2e": o2[90.0]["e2e_qps"],
+                     "at_recall_95": {"L": o2[95.0]["L"], "recall_at_10": round(o2[95.0]["recall"], 2), "value": o2[95.0]["qps"],
+                                      "e2e": o2[95.0]["e2e_qps"]},
+                     "roofline": roofline_of(o2[90.0], w2, name, peak_gbs, peak_src)}
+                if name == "sift1m" and not args.no_ref_cuda:
+                    ref = reference_cuda_run(pf2, w2, paths2, q2[: w2["q"]], o2[90.0]["L"], g2, gd2, local)
+                    if ref:
+                        e["reference_cuda_b200"] = ref
+                line["other_configs"][name] = e
+            except (Exception, SystemExit) as ex:  # noqa: BLE001
+                line["other_configs"][name] = {"error": str(ex)[:300]}
     print(json.dumps(line), flush=True)
+
+
+def extra_ranks_done(world):
+    return
+
+
+# ----------------------------------------------------------------------------------------------------
+# C5: graph rows sharded over the GPUs' HBM, NVLink P2P fetch inside the kernel (torchrun, G = world)
+# ----------------------------------------------------------------------------------------------------
+def run_sharded(args, wl, device, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import bang_b200  # noqa: F401
+    from bang_b200 import api, build_sharded, recall, sharding
+    if world < 2:
+        raise SystemExit("the sharded workloads run under torchrun with >= 2 ranks (one per GPU)")
+    Q, N = wl["q"], wl["n"]
+    t_all = time.time()
+    s = api.BANGSearch("uint8", wl["mode"], device=local)
+    s.set_sharding(rank, world)
+    n_gt = min(1000, Q)
+    ownership = os.environ.get("C5_OWNERSHIP", "mod")
+    my_q, gt_ids, gt_d, medoid, T = build_sharded.build_and_load(s, N, wl["d"], Q, n_gt, P_per_rank=int(os.environ.get("C5_SHARDS_PER_RANK", "4")),
+                                                                 passes=int(os.environ.get("C5_PASSES", "2")), ownership=ownership)
+    my_idx = T.pop("my_idx")
+    T.pop("home", None)
+    Qall = Q * world
+    Qmine = len(my_q)
+    sharding.exchange_shards(s, rank, world)
+    info = s.info()
+    if rank == 0:
+        log(f"[bench c5] N={N} built+loaded in {time.time() - t_all:.1f}s {T}; per-GPU HBM {info.device_bytes / 2**30:.1f} GiB")
+    s.set_dists_layout(api.DISTS_QUERY_MAJOR)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def run_L(L, steps, warmup):
+        s.bang_set_searchparams(K, L)
+        s.bang_alloc(Qmine)
+        ms, e2e = [], []
+        for r in range(warmup + steps):
+            s.bang_init(Qmine)
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ids, d = s.bang_query(my_q)
+            e2e.append((time.perf_counter() - t0) * 1e3)
+            ms.append(s.last_timing().kernel_ms)
+        st = s.last_stats(Qmine)
+        s.bang_free()
+        k_ms = float(np.mean(sharding.max_over_ranks(ms[warmup:], device=device)))
+        e_ms = float(np.mean(sharding.max_over_ranks(e2e[warmup:], device=device)))
+        parts = [None] * world
+        keep = my_idx < n_gt
+        dist.all_gather_object(parts, (my_idx[keep], ids[keep]))
+        rec = None
+        if rank == 0:
+            got = np.zeros((n_gt, K), dtype=np.uint64)
+            for idx_r, ids_r in parts:
+                got[idx_r] = ids_r
+            rec = recall.calculate_recall(gt_ids[:n_gt], gt_d[:n_gt], got, K)
+        box = [rec]
+        dist.broadcast_object_list(box, src=0)
+        return dict(L=L, recall=box[0], ms=k_ms, e2e_ms=e_ms, stats=st, my_ms=float(np.mean(ms[warmup:])))
+
+    # operating points: coarse sweep with short runs, then the timed runs
+    curve, found = [], {}
+    for L in ([args.L] if args.L else (64, 96, 128, 152, 176, 200, 256, 320, 400, 512)):
+        r = run_L(L, 1, 1)
+        curve.append((L, round(r["recall"], 2), round(r["ms"], 2)))
+        for t in (90.0, 95.0):
+            if t not in found and r["recall"] >= t:
+                found[t] = L
+        if len(found) == 2:
+            break
+    if args.L:
+        found = {90.0: args.L, 95.0: args.L95 or args.L}
+    res = {t: run_L(found[t], args.steps, args.warmup) for t in (90.0, 95.0) if t in found}
+    clocks = sampler.stop()
+    if rank == 0:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        line = {"metric": METRIC, "unit": "QPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8 codes / fp32 ADC sums",
+                "data": "synthetic clustered (Gaussian mixture), index built on the GPUs by the committed sharded builder (DiskANN-style partition + merge)",
+                "config": {"workload": label(wl, Qall), "recall_curve_L_recall_ms": curve, "recall_queries": n_gt, "ownership": ownership,
+                           "parallelism": f"graph rows sharded id mod {world} over the GPUs' HBM, PQ codes replicated, P2P loads inside the kernel; "
+                                          f"one batch of {Q} queries per GPU; no collective inside the loop",
+                           "per_gpu_hbm_gib": round(info.device_bytes / 2**30, 1), "build_seconds": T, "kernel_source_hash": kernel_source_hash()},
+                "gpu_launches": args.steps, "clocks": clocks}
+        if 90.0 in res:
+            r = res[90.0]
+            st = r["stats"]
+            hops, sdeg, nc = (st[k_].astype(np.int64) for k_ in ("hops", "sum_deg", "n_cand"))
+            rows_b = 4 * hops + 4 * sdeg + hops * wl["d"]          # adjacency + re-rank vectors: (G-1)/G of it crosses NVLink
+            nvl = rows_b * (world - 1) / world
+            hbm = nc * wl["m"] + rows_b / world + wl["d"] + 8 * K
+            t = r["my_ms"] * 1e-3
+            line.update({"value": Qall / (r["ms"] * 1e-3), "ms_per_step": r["ms"],
+                         "e2e": {"value": Qall / (r["e2e_ms"] * 1e-3), "unit": "QPS", "ms_per_step": r["e2e_ms"],
+                                 "h2d_bytes_per_step": int(Qall * wl["d"]), "d2h_bytes_per_step": int(Qall * K * 12)},
+                         "roofline": {"bound": "hbm", "achieved": float(hbm.sum()) / t / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                                      "frac": float(hbm.sum()) / t / 1e9 / peak_gbs, "traffic": None,
+                                      "hbm_bytes_per_query": float(hbm.mean()), "nvlink_bytes_per_query": float(nvl.mean()),
+                                      "nvlink": {"achieved": float(nvl.sum()) / t / 1e9, "peak": 900.0, "unit": "GB/s per direction",
+                                                 "frac": float(nvl.sum()) / t / 1e9 / 900.0},
+                                      "hops_per_query": float(hops.mean()), "candidates_per_query": float(nc.mean()),
+                                      "kernel": "bang_search_kernel (fused traversal, 1 launch per step, peer rows over NVLink)"}})
+            line["config"].update({"L_at_recall_90": r["L"], "recall_at_10": round(r["recall"], 2)})
+        if 95.0 in res:
+            r = res[95.0]
+            line["at_recall_95"] = {"L": r["L"], "recall_at_10": round(r["recall"], 2), "value": Qall / (r["ms"] * 1e-3), "ms_per_step": r["ms"],
+                                    "e2e": Qall / (r["e2e_ms"] * 1e-3)}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    s.bang_unload()
+    dist.barrier()
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -408,46 +642,44 @@ def run_reference(args):
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import bang_b200  # noqa: F401
-    from bang_b200 import api, formats, recall
+    import bang_b200  # noqa: F401   (pure-Python package import: formats / recall; the CUDA library is never loaded here)
+    from bang_b200 import formats, recall
     import oracle as O
-    wl = dict(WORKLOADS[args.workload])
-    if args.n:
-        wl["n"] = args.n
-    if args.q:
-        wl["q"] = args.q
-    workdir = args.workdir or os.path.join(tempfile.gettempdir(), "bang_b200_bench")
-    os.makedirs(workdir, exist_ok=True)
-    device = "cpu"
-    try:
-        import torch
-        if torch.cuda.is_available():
-            device = torch.device("cuda", 0)
-    except Exception:
-        pass
-    prefix = make_index(wl, workdir, device, args.builder, 0, 1)
+    wl = workload(args)
+    if wl.get("sharded"):
+        print(json.dumps({"impl": "reference", "unavailable": "the sharded configuration holds no host copy of the 10^9-point index (388 GB); "
+                                                              "the host-core arm runs on the single-GPU configurations"}), flush=True)
+        return
+    prefix = find_cached(wl, args)
+    if not prefix:   # the index builder is this repo's GPU code: it runs in a child process, this one only reads the files
+        cmd = [sys.executable, os.path.abspath(__file__), "--prepare", "--workload", args.workload, "--builder", args.builder]
+        if args.workdir:
+            cmd += ["--workdir", args.workdir]
+        if args.n:
+            cmd += ["--n", str(args.n)]
+        if args.q:
+            cmd += ["--q", str(args.q)]
+        env = {k_: v for k_, v in os.environ.items() if k_ not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+        r = subprocess.run(cmd, env=env, stdout=subprocess.DEVNULL)
+        prefix = find_cached(wl, args)
+        if r.returncode != 0 or not prefix:
+            print(json.dumps({"impl": "reference", "unavailable": "index preparation failed (bench.py --prepare)"}), flush=True)
+            return
+    meta = read_meta(prefix)
     paths = formats.IndexPaths(prefix)
-    queries = formats.read_bin(paths.query, api.NP[wl["dtype"]])[: wl["q"]]
+    npdt = {"uint8": np.uint8, "int8": np.int8, "float": np.float32}[wl["dtype"]]
+    queries = formats.read_bin(paths.query, npdt)[: wl["q"]]
     gt_ids, gt_d = formats.read_truthset(paths.truth)
-    ox = O.OracleIndex.from_files(prefix, with_pq=wl["mode"] != "exact")
+    ox = O.OracleIndex.from_files(prefix, with_pq=wl["mode"] != "exact", mmap=True)
     mode = {"base": O.MODE_BASE, "inmemory": O.MODE_INMEMORY, "exact": O.MODE_EXACT}[wl["mode"]]
     cores = os.cpu_count() or 1
-    # operating point: same sweep, on a bounded sample
+    L90 = args.L or meta["L90"]   # the operating point of the b200 arm: one sweep over the full batch, cached by --prepare
     ns = min(len(queries), 512)
-    L90 = args.L
-    if not L90:
-        for L in L_SWEEP:
-            ids, _ = ox.search(queries[:ns], K, L, mode=mode, nthreads=cores)
-            if recall.calculate_recall(gt_ids[:ns], gt_d[:ns], ids, K) >= 90.0:
-                L90 = L
-                break
-    if not L90:
-        L90 = L_SWEEP[-1]
-    # bounded sample per step: ~ (60 s total) / (steps + warmup)
+    ox.search(queries[:ns], K, L90, mode=mode, nthreads=cores)  # pages the touched part of the mapped index in
     t0 = time.perf_counter()
     ox.search(queries[:ns], K, L90, mode=mode, nthreads=cores)
     per_q = (time.perf_counter() - t0) / ns
-    budget = 60.0 / max(1, args.steps + args.warmup)
+    budget = 60.0 / max(1, args.steps + args.warmup)   # bounded sample per step: ~60 s in total
     n = int(min(len(queries), max(ns, budget / per_q)))
     for _ in range(args.warmup):
         ox.search(queries[:n], K, L90, mode=mode, nthreads=cores)
@@ -458,18 +690,25 @@ def run_reference(args):
         ts.append(time.perf_counter() - t0)
     rec = recall.calculate_recall(gt_ids[:n], gt_d[:n], ids, K)
     qps = n / float(np.mean(ts))
-    Qtot = len(queries)
-    sample = f"{n} of {Qtot} queries per step at L={L90}; oracle/bang_oracle.c (CPU restatement of the reference's search), OpenMP over queries"
-    line = {"impl": "reference", "metric": "QPS at recall@10 >= 0.90 (batched greedy Vamana search)", "value": qps, "unit": "QPS",
+    Qtot = wl["q"] * max(1, args.gpus) if args.scaling == "weak" else wl["q"]
+    sample = f"{n} of {wl['q']} queries per step at L={L90}; oracle/bang_oracle.c (CPU restatement of the reference's search), OpenMP over queries"
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "QPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ts)) * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic clustered",
-            "config": {"workload": f"{wl['label']}: N={wl['n']} D={wl['d']} {wl['dtype']} R=64 "
-                                   + (f"PQ m={wl['m']}" if wl["m"] else "no PQ") + f", Q={Qtot}, k={K}, mode={wl['mode']}",
-                       "L_at_recall_90": L90, "recall_at_10": round(rec, 2),
-                       "note": "the reference is GPU-only; its search logic runs here on the host cores (kind=port)"},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic clustered",
+            "config": {"workload": label(wl, Qtot), "L_at_recall_90": L90, "recall_at_10": round(rec, 2),
+                       "note": "the reference is GPU-only; its search logic runs here on the host cores (kind=port); one host, so the value does not grow with --gpus"},
             "cpu_baseline": {"value": qps, "unit": "QPS", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "QPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def workload(args) -> dict:
+    wl = dict(WORKLOADS[args.workload])
+    if args.n:
+        wl["n"] = args.n
+    if args.q:
+        wl["q"] = args.q
+    return wl
 
 
 def main():
@@ -478,16 +717,23 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sift1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--prepare", action="store_true", help="build + cache the index files and operating points, then exit")
     ap.add_argument("--n", type=int, default=0, help="override the number of base points (parity/debug runs only)")
     ap.add_argument("--q", type=int, default=0)
-    ap.add_argument("--L", type=int, default=0, help="fix the worklist length instead of sweeping")
+    ap.add_argument("--L", type=int, default=0, help="fix the worklist length instead of using the cached sweep")
     ap.add_argument("--L95", type=int, default=0)
     ap.add_argument("--builder", default="auto", choices=["auto", "gpu", "cpu"])
     ap.add_argument("--workdir", default="")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the unmodified reference CUDA build on C2 (other_configs.sift1m)")
+    ap.add_argument("--ref-cuda", action="store_true", help="also run the unmodified reference CUDA build on the main workload")
+    ap.add_argument("--no-extra", action="store_true", help="skip other_configs (C2, C3)")
     args = ap.parse_args()
+    if args.prepare:
+        prepare(workload(args), args)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

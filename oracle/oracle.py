@@ -96,16 +96,21 @@ class OracleIndex:
                          p(self.disk), p(self.codes), p(self.pivots), p(self.centroid), p(self.chunk_offsets))
 
     @classmethod
-    def from_files(cls, prefix: str, with_pq: bool = True):
+    def from_files(cls, prefix: str, with_pq: bool = True, mmap: bool = False):
+        """mmap: map `_disk.bin` and the PQ codes instead of reading them (indices of tens of GB: no second copy in RAM)."""
         import sys
         sys.path.insert(0, os.path.dirname(_HERE))
         import bang_b200  # noqa: F401
         from bang_b200 import formats
         paths = formats.IndexPaths(prefix)
         meta = formats.read_disk_metadata(paths.disk_meta)
-        disk = np.fromfile(paths.disk, dtype=np.uint8)
+        disk = np.memmap(paths.disk, dtype=np.uint8, mode="r") if mmap else np.fromfile(paths.disk, dtype=np.uint8)
         codes = piv = cen = offs = None
-        if with_pq:
+        if with_pq and mmap:
+            hdr = np.fromfile(paths.pq_compressed, dtype=np.int32, count=2)
+            codes = np.memmap(paths.pq_compressed, dtype=np.uint8, mode="r", offset=8, shape=(int(hdr[0]), int(hdr[1])))
+            piv, cen, offs = formats.read_pq_pivots_new(paths.pq_pivots, meta.D, codes.shape[1])
+        elif with_pq:
             codes = formats.read_bin(paths.pq_compressed, np.uint8)
             piv, cen, offs = formats.read_pq_pivots_new(paths.pq_pivots, meta.D, codes.shape[1])
         return cls(disk, meta.dtype, meta.D, meta.R, meta.medoid, codes, piv, cen, offs)
