@@ -35,7 +35,8 @@ ABI_SYMBOLS = [
     "bang_b200_load_device_codes", "bang_b200_load_device_codes_at", "bang_b200_load_device_end", "bang_b200_set_searchparams", "bang_b200_alloc",
     "bang_b200_init", "bang_b200_query", "bang_b200_free", "bang_b200_unload", "bang_b200_set_dists_layout",
     "bang_b200_query_device", "bang_b200_pq_table", "bang_b200_info", "bang_b200_last_stats",
-    "bang_b200_last_timing", "bang_b200_last_error", "bang_load_c", "bang_set_searchparams_c", "bang_query_c",
+    "bang_b200_last_timing", "bang_b200_last_error", "bang_b200_bruteforce_gt", "bang_b200_pq_train", "bang_b200_pq_encode",
+    "bang_b200_prep_last_error", "bang_load_c", "bang_set_searchparams_c", "bang_query_c",
     "bang_unload_c",
 ]
 
@@ -100,6 +101,10 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         "bang_b200_last_stats": (ci, [vp, vp, vp, vp]),
         "bang_b200_last_timing": (ci, [vp, ctypes.POINTER(Timing)]),
         "bang_b200_last_error": (ctypes.c_char_p, []),
+        "bang_b200_bruteforce_gt": (ci, [ci, vp, u64, u32, vp, u32, u32, u64, vp, vp, vp]),
+        "bang_b200_pq_train": (ci, [ci, vp, u64, u32, vp, u32, u32, u64, u64, vp, vp, vp]),
+        "bang_b200_pq_encode": (ci, [ci, vp, u64, u32, vp, vp, vp, u32, vp, vp]),
+        "bang_b200_prep_last_error": (ctypes.c_char_p, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -265,6 +270,67 @@ class BANGSearch:
         out = Timing()
         self._check(self._lib.bang_b200_last_timing(self._h, ctypes.byref(out)))
         return out
+
+
+# ---- data preparation kernels (csrc/prep_kernels.cu): CUDA tensors in, see include/bang_b200.h ----
+def _prep_check(lib, rc: int) -> None:
+    if rc != 0:
+        raise BangError(rc, lib.bang_b200_prep_last_error().decode())
+
+
+def _torch_dtype_name(t) -> str:
+    import torch
+    return {torch.uint8: "uint8", torch.int8: "int8", torch.float32: "float"}[t.dtype]
+
+
+def bruteforce_gt(base, queries, k: int, id_offset: int = 0):
+    """Exact kNN ground truth on the GPU.  base [n][D], queries [nq][D]: contiguous CUDA tensors of one element type.
+    Returns CUDA tensors (ids int64 [nq][k] holding u32 values, dists float32 [nq][k]) ordered by (distance, id)."""
+    import torch
+    assert base.is_cuda and queries.is_cuda and base.is_contiguous() and queries.is_contiguous() and base.dtype == queries.dtype
+    lib = load_library()
+    nq = queries.shape[0]
+    ids = torch.empty((nq, k), dtype=torch.int32, device=base.device)
+    dists = torch.empty((nq, k), dtype=torch.float32, device=base.device)
+    with torch.cuda.device(base.device):
+        st = torch.cuda.current_stream(base.device).cuda_stream
+        _prep_check(lib, lib.bang_b200_bruteforce_gt(DT[_torch_dtype_name(base)], base.data_ptr(), base.shape[0], base.shape[1],
+                                                    queries.data_ptr(), nq, k, id_offset, ids.data_ptr(), dists.data_ptr(), st))
+    return ids.to(torch.int64) & 0xFFFFFFFF, dists
+
+
+def pq_train(base, chunk_offsets: np.ndarray, iters: int = 12, max_train: int = 65536, seed: int = 0x50):
+    """k-means PQ pivots on the GPU.  Returns (pivots f32 [256][D], centroid f32 [D]) as numpy arrays."""
+    import torch
+    assert base.is_cuda and base.is_contiguous()
+    lib = load_library()
+    D = base.shape[1]
+    offs = np.ascontiguousarray(chunk_offsets, dtype=np.uint32)
+    piv = np.zeros((256, D), dtype=np.float32)
+    cen = np.zeros(D, dtype=np.float32)
+    with torch.cuda.device(base.device):
+        st = torch.cuda.current_stream(base.device).cuda_stream
+        _prep_check(lib, lib.bang_b200_pq_train(DT[_torch_dtype_name(base)], base.data_ptr(), base.shape[0], D, offs.ctypes.data,
+                                               len(offs) - 1, iters, max_train, seed, piv.ctypes.data, cen.ctypes.data, st))
+    return piv, cen
+
+
+def pq_encode(base, pivots: np.ndarray, centroid: np.ndarray, chunk_offsets: np.ndarray):
+    """PQ codes on the GPU: CUDA uint8 tensor [n][m]."""
+    import torch
+    assert base.is_cuda and base.is_contiguous()
+    lib = load_library()
+    D = base.shape[1]
+    offs = np.ascontiguousarray(chunk_offsets, dtype=np.uint32)
+    piv = np.ascontiguousarray(pivots, dtype=np.float32)
+    cen = np.ascontiguousarray(centroid, dtype=np.float32)
+    m = len(offs) - 1
+    codes = torch.empty((base.shape[0], m), dtype=torch.uint8, device=base.device)
+    with torch.cuda.device(base.device):
+        st = torch.cuda.current_stream(base.device).cuda_stream
+        _prep_check(lib, lib.bang_b200_pq_encode(DT[_torch_dtype_name(base)], base.data_ptr(), base.shape[0], D, piv.ctypes.data,
+                                                cen.ctypes.data, offs.ctypes.data, m, codes.data_ptr(), st))
+    return codes
 
 
 def algorithmic_bytes(stats: dict, mode: str, D: int, elem_size: int, n_chunks: int, k: int) -> np.ndarray:

@@ -113,7 +113,7 @@ def merge_lists(adj_own: torch.Tensor, rows: torch.Tensor, new: torch.Tensor, gi
 
 def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries: int, m: int = 32, P_per_rank: int = 4,
                    chunk: int = 1 << 22, L_build: int = 64, passes: int = 2, seed: int = synth.BASE_SEED,
-                   ownership: str = "mod", device=None, build_fn=None, shard_slack: float = 1.30):
+                   ownership: str = "mod", device=None, build_fn=None, shard_slack: float = 1.30, gt_fn=None):
     """Builds the sharded index on the GPUs and loads this rank's shard into `search` (an api.BANGSearch with
     set_sharding(rank, world) already called).  Returns (queries_for_this_rank u8 [q][D], gt_ids [n_gt][100] or None
     on ranks != 0, gt_dists, medoid, timings dict).
@@ -143,8 +143,12 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
     qg.manual_seed(synth.QUERY_SEED ^ seed)
     qa = torch.randint(0, n_clusters, (G * n_queries_per_rank,), generator=qg, device=dev)
     queries = (centers[qa] + SIGMA_U8 * torch.randn(qa.numel(), D, generator=qg, device=dev)).round_().clamp_(0, 255).to(torch.uint8)
-    gt_q = queries[:n_gt_queries].float()
-    gt_qn = (gt_q ** 2).sum(1)
+    gt_q_raw = queries[:n_gt_queries].contiguous()
+    if gt_fn is None and dev.type != "cuda":   # CPU dry run: plain torch (uint8 distances are exact in fp32)
+        def gt_fn(x, q, k):
+            d2 = torch.cdist(q.float(), x.float()) ** 2
+            dd, ii = torch.topk(d2.round(), k, dim=1, largest=False)
+            return dd, ii
     # partition centres: Lloyd on the mixture centres, rank 0 decides
     pc = centers[torch.randperm(n_clusters, device=dev)[:P]].clone()
     if rank == 0:
@@ -224,13 +228,14 @@ def build_and_load(search, N: int, D: int, n_queries_per_rank: int, n_gt_queries
         if float(v) < med_d:
             med_d, med_i = float(v), int(gid[int(i)])
         if c % G == rank and n_gt_queries:
-            xn = (xf * xf).sum(1)
-            d2 = gt_qn[:, None] + xn[None, :] - 2.0 * (gt_q @ xf.T)   # fp32, exact for uint8 data (all terms < 2^24)
-            dd, ii = torch.topk(d2, min(100, n), dim=1, largest=False)
+            if gt_fn is not None:   # (CPU dry runs of the host logic: tests/test_build_sharded_dryrun.py)
+                dd, ii = gt_fn(x, gt_q_raw, min(100, n))
+            else:                   # exact kNN of the chunk by the library's brute-force kernel (csrc/prep_kernels.cu)
+                from . import api
+                ii, dd = api.bruteforce_gt(x, gt_q_raw, min(100, n))
             cat_d = torch.cat([best_d, dd], 1); cat_i = torch.cat([best_i, gid[ii]], 1)
             sel = torch.topk(cat_d, 100, dim=1, largest=False)[1]
             best_d = torch.gather(cat_d, 1, sel); best_i = torch.gather(cat_i, 1, sel)
-            del d2
         del x, xf, d2p, top2, gid
     medoid = med_i
     n_virtual = N

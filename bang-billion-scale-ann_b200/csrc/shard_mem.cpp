@@ -98,9 +98,9 @@ int map_handle(ShardMem* m, CUmemGenericAllocationHandle h, size_t padded, size_
 
 }  // namespace
 
-bool shard_vmm_requested() {
+bool shard_vmm_requested() {  // default for sharded indices; BANG_B200_SHARD_VMM=0 selects the CUDA-IPC scheme
   const char* e = getenv("BANG_B200_SHARD_VMM");
-  return e && *e && strcmp(e, "0") != 0;
+  return !(e && strcmp(e, "0") == 0);
 }
 
 int shard_alloc(ShardMem* m, size_t bytes, int device, bool vmm, std::string* err) {

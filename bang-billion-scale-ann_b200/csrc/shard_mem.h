@@ -6,8 +6,9 @@
 //           + cuMemAddressReserve / cuMemMap / cuMemSetAccess on both sides; the descriptor travels between the
 //           processes over a Unix-domain socket (SCM_RIGHTS; bang_b200/sharding.py).  The owner controls the
 //           physical granularity and both sides the alignment of the mapping, which the legacy scheme leaves to the
-//           driver (profiles/r1_c5.md finding 2).
-// BANG_B200_SHARD_VMM=1 selects vmm for sharded indices; everything else uses legacy.  The driver API is reached
+//           driver.  Measured (profiles/r2_c5.md): the traversal over peer rows mapped this way runs within 4 % of
+//           the single-GPU time, while the legacy mappings have a slow mode at some sizes (1.7x at 9 M points on 2 GPUs).
+// Sharded indices use vmm (BANG_B200_SHARD_VMM=0 selects legacy); unsharded ones plain cudaMalloc.  The driver API is reached
 // through cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda.
 #pragma once
 #include <cstddef>
@@ -25,7 +26,7 @@ struct ShardMem {
   bool imported = false;    // legacy: opened with cudaIpcOpenMemHandle
 };
 
-bool shard_vmm_requested();  // BANG_B200_SHARD_VMM set and not "0"
+bool shard_vmm_requested();  // true unless BANG_B200_SHARD_VMM=0
 
 // All return 0 on success; otherwise a negative value and *err describes the failure.
 int shard_alloc(ShardMem* m, size_t bytes, int device, bool vmm, std::string* err);

@@ -2,9 +2,9 @@
 path: queries are independent.
 
 * replicated index (<= 100 M points): every rank loads the whole index and searches its own batch;
-* sharded graph (1 B points): rank r keeps rows with id % G == r; the 64-byte CUDA IPC handles of the shards
-  are exchanged once (all_gather_object) and imported, after which the traversal kernel reads peers' rows
-  with P2P loads over NVLink (replaces BANG_Base's host-RAM graph, bang_search.cu:709-845).
+* sharded graph (1 B points): rank r keeps rows with id % G == r; the shards (CUDA virtual-memory allocations) are
+  exchanged once as file descriptors and mapped, after which the traversal kernel reads peers' rows with P2P
+  loads over NVLink (replaces BANG_Base's host-RAM graph, bang_search.cu:709-845).
 """
 from __future__ import annotations
 
@@ -93,13 +93,15 @@ def exchange_fds(fd: int, payload: bytes, rank: int, world: int, tag: str | None
 
 def exchange_shards(search, rank: int, world: int) -> None:
     """After bang_load on every rank with set_sharding(rank, world): import every peer's graph shard.
-    Legacy scheme: 64-byte CUDA IPC handles through all_gather_object.  BANG_B200_SHARD_VMM=1 (set before the load):
-    the rows are VMM allocations, shared as file descriptors (exchange_fds)."""
+    Default: the rows are CUDA virtual-memory (VMM) allocations, shared as file descriptors (exchange_fds) — peer
+    reads of rows mapped this way run at the speed of local ones, while cudaMalloc + CUDA-IPC mappings have a slow
+    mode at some sizes (9 M points on 2 GPUs: 14.5 ms against 8.4 ms, profiles/r2_c5.md).  BANG_B200_SHARD_VMM=0 (set
+    before the load) selects the CUDA-IPC scheme: 64-byte handles through all_gather_object."""
     import os
     import torch.distributed as dist
     if world == 1:
         return
-    if os.environ.get("BANG_B200_SHARD_VMM", "0") not in ("", "0"):
+    if os.environ.get("BANG_B200_SHARD_VMM", "1") != "0":
         fd, nbytes = search.export_shard_fd()
         got = exchange_fds(fd, nbytes.to_bytes(8, "little"), rank, world)
         os.close(fd)

@@ -11,6 +11,8 @@ pivots stored as float[256][D].
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -89,7 +91,14 @@ def chunk_offsets_even(d: int, m: int) -> np.ndarray:
 
 @torch.no_grad()
 def train_pq(base: torch.Tensor, m: int, iters: int = 12, max_train: int = 65536, seed: int = PQ_SEED):
-    """Returns pivots float32[256][D], centroid float32[D], chunk_offsets u32[m+1] (numpy)."""
+    """Returns pivots float32[256][D], centroid float32[D], chunk_offsets u32[m+1] (numpy).
+    CUDA tensors go through the library's k-means kernels (csrc/prep_kernels.cu); the torch code below is the host
+    path of the small committed fixtures (tests/golden/make_fixture.py) and the reference the kernels are tested against."""
+    if base.is_cuda and not os.environ.get("BANG_B200_TORCH_PREP"):
+        from . import api
+        offs = chunk_offsets_even(base.shape[1], m)
+        piv, cen = api.pq_train(base.contiguous(), offs, iters=iters, max_train=max_train, seed=seed)
+        return piv, cen, offs
     dev = base.device
     n, d = base.shape
     g = _gen(seed, dev)
@@ -129,6 +138,9 @@ def train_pq(base: torch.Tensor, m: int, iters: int = 12, max_train: int = 65536
 
 @torch.no_grad()
 def encode_pq(base: torch.Tensor, pivots: np.ndarray, centroid: np.ndarray, offs: np.ndarray) -> torch.Tensor:
+    if base.is_cuda and not os.environ.get("BANG_B200_TORCH_PREP"):
+        from . import api
+        return api.pq_encode(base.contiguous(), pivots, centroid, offs)
     dev = base.device
     piv = torch.from_numpy(pivots).to(dev)
     cen = torch.from_numpy(centroid).to(dev)
@@ -156,7 +168,12 @@ def brute_force_gt(base: torch.Tensor, queries: torch.Tensor, k: int, block: int
     then the final k are re-scored with direct (a-b)^2 sums so distances are the exact ones the
     search kernels produce (integers for u8/i8 inputs).  Queries are processed q_block at a time so the
     distance tile stays at q_block x block floats (8 GB).
+    CUDA tensors go through the library's brute-force kernels (csrc/prep_kernels.cu); this torch code is the host path.
     """
+    if base.is_cuda and not os.environ.get("BANG_B200_TORCH_PREP"):
+        from . import api
+        ids, d = api.bruteforce_gt(base.contiguous(), queries.contiguous(), k)
+        return ids.cpu().numpy().astype(np.uint32), d.cpu().numpy()
     if queries.shape[0] > q_block:
         parts = [brute_force_gt(base, queries[s:s + q_block], k, block, q_block) for s in range(0, queries.shape[0], q_block)]
         return np.concatenate([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts], 0)

@@ -144,6 +144,27 @@ int bang_b200_last_timing(bang_handle_t h, bang_b200_timing_t* out);
 
 const char* bang_b200_last_error(void);
 
+/* ---- data preparation on the GPU (csrc/prep_kernels.cu) -------------------------------------------------------
+ * The reference takes its ground truth and its PQ files from DiskANN's tools (`compute_groundtruth`,
+ * `build_disk_index`; README.md:46-58).  These entry points produce the same arrays with hand-written kernels, for
+ * indices built on the box.  All pointers prefixed d_ are DEVICE pointers; `cuda_stream` is a cudaStream_t or NULL;
+ * the calls return after the work is done.  Errors: bang_b200_prep_last_error(). */
+/* Exact k nearest neighbours (squared L2) of nq queries among n base rows, k <= 128: d_ids u32[nq][k] (row index +
+ * id_offset), d_dists float[nq][k], both ordered by (distance, id) — the two halves of the truthset file
+ * (test_driver.cpp:238-272).  u8/i8 distances are exact integers. */
+int bang_b200_bruteforce_gt(bang_dtype_t dtype, const void* d_base, uint64_t n, uint32_t D, const void* d_queries, uint32_t num_queries,
+                            uint32_t k, uint64_t id_offset, uint32_t* d_ids, float* d_dists, void* cuda_stream);
+/* PQ training: centroid = column means of the base (host float[D] out); pivots = 256 k-means centres per chunk of the
+ * centred data (host float[256][D] out, the layout of `_pq_pivots.bin`), Lloyd iterations on at most max_train rows
+ * spread evenly over the base (0 = all rows).  chunk_offsets: host u32[n_chunks+1], chunks of 1..32 dimensions. */
+int bang_b200_pq_train(bang_dtype_t dtype, const void* d_base, uint64_t n, uint32_t D, const uint32_t* chunk_offsets, uint32_t n_chunks,
+                       uint32_t iters, uint64_t max_train, uint64_t seed, float* pivots, float* centroid, void* cuda_stream);
+/* PQ encoding: d_codes u8[n][n_chunks] = index of the closest pivot of every chunk (first minimum) — the payload of
+ * `_pq_compressed.bin`.  pivots / centroid / chunk_offsets are host arrays as above. */
+int bang_b200_pq_encode(bang_dtype_t dtype, const void* d_base, uint64_t n, uint32_t D, const float* pivots, const float* centroid,
+                        const uint32_t* chunk_offsets, uint32_t n_chunks, uint8_t* d_codes, void* cuda_stream);
+const char* bang_b200_prep_last_error(void);
+
 /* The reference's own C API (bang.h:89-101, `#if 0` there): one process-wide uint8 instance. */
 int bang_load_c(char* indexfile_path_prefix);
 void bang_set_searchparams_c(int recall, int worklist_length, int nDistFunc);

@@ -247,16 +247,19 @@ def test_against_reference_cuda_build(fixtures, name, tmp_path):
     assert abs(r_ref - r_new) <= 0.1 + 1e-9
 
 
-def test_sharded_graph_p2p_two_gpus():
-    """Graph rows sharded over 2 GPUs, peers read with P2P loads in the kernel: bit-exact vs the oracle."""
+@pytest.mark.parametrize("scheme", ["vmm", "ipc"])
+def test_sharded_graph_p2p_two_gpus(scheme):
+    """Graph rows sharded over 2 GPUs, peers read with P2P loads in the kernel: bit-exact vs the oracle, for both ways
+    of sharing the rows between the processes (VMM + file descriptors, the default; cudaMalloc + CUDA IPC)."""
     import sys
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs on one box")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BANG_B200_SHARD_VMM="1" if scheme == "vmm" else "0")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "p2p_check.py")],
-                       capture_output=True, text=True, timeout=600)
+                        "127.0.0.1", "--master-port", "29517" if scheme == "vmm" else "29518", os.path.join(root, "tests", "p2p_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ids == oracle: True") == 6
 

@@ -24,6 +24,7 @@ class _FakeSearch:
     def __init__(self, rank):
         self.rank = rank
         self.imported = {}
+        self.imported_fd = {}
 
     def export_shard(self):
         return bytes([self.rank]) * 64
@@ -31,6 +32,18 @@ class _FakeSearch:
     def import_shard(self, shard, handle):
         assert len(handle) == 64
         self.imported[shard] = handle
+
+    # VMM scheme (the default): the shard travels as an open file descriptor + its size
+    def export_shard_fd(self):
+        import tempfile
+        self._f = tempfile.TemporaryFile()
+        self._f.write(bytes([self.rank]) * 64)
+        self._f.flush()
+        return os.dup(self._f.fileno()), 4096 + self.rank
+
+    def import_shard_fd(self, shard, fd, nbytes):
+        assert nbytes == 4096 + shard
+        self.imported_fd[shard] = os.pread(fd, 64, 0)
 
 
 def _worker(rank, world, port, out):
@@ -43,7 +56,11 @@ def _worker(rank, world, port, out):
         allr = sharding.gather_rows(mine)
         t = sharding.max_over_ranks([1.0 + rank, 5.0 - rank])
         fs = _FakeSearch(rank)
+        sharding.exchange_shards(fs, rank, world)            # default scheme: VMM shards as file descriptors
+        assert sorted(fs.imported_fd) == [1 - rank] and fs.imported_fd[1 - rank] == bytes([1 - rank]) * 64 and not fs.imported
+        os.environ["BANG_B200_SHARD_VMM"] = "0"              # CUDA-IPC scheme: 64-byte handles
         sharding.exchange_shards(fs, rank, world)
+        del os.environ["BANG_B200_SHARD_VMM"]
         # file descriptors between the ranks (the transport of VMM shards): every rank shares an open temp file
         import tempfile
         with tempfile.TemporaryFile() as f:
