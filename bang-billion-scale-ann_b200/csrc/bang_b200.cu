@@ -266,11 +266,11 @@ static int upload_pq(bang_b200_ctx* c, const PQHost& pq) {
   if (pq.chunk_off.back() != D) return set_err(BANG_E_FORMAT, "chunk offsets do not end at D");
   for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
     if (pq.chunk_off[i] > pq.chunk_off[i + 1]) return set_err(BANG_E_FORMAT, "chunk offsets not monotone");
-  // uniform chunk size (4: SIFT 128/32, GIST...; 3: DEEP 96/32) selects a compile-time ADC path
+  // 32 chunks of one size (4: SIFT 128/32; 3: DEEP 96/32) select a compile-time ADC path; everything else the general one
   c->chunk4 = pq.chunk_off.size() > 1 ? pq.chunk_off[1] - pq.chunk_off[0] : 0;
   for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
     if (pq.chunk_off[i + 1] - pq.chunk_off[i] != c->chunk4) c->chunk4 = 0;
-  if (c->chunk4 != 4 && c->chunk4 != 3) c->chunk4 = 0;
+  if ((c->chunk4 != 4 && c->chunk4 != 3) || c->n_chunks != 32) c->chunk4 = 0;  // the CS kernels assume one full 32-chunk group
   CUDA_TRY(cudaMalloc(&c->d_piv, pq.pivots.size() * 4));
   CUDA_TRY(cudaMemcpy(c->d_piv, pq.pivots.data(), pq.pivots.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&c->d_pivT, pivT.size() * 4));

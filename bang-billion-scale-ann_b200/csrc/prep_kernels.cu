@@ -9,7 +9,7 @@
 //
 // Ground truth.  A query tile x base tile kernel computes all pair distances with 4x4 register blocking (u8/i8:
 // packed dp4a dot products, distance = |q|^2 + |b|^2 - 2 q.b in exact integers; float: fmaf of differences) and
-// appends only the pairs at or below the query's current k-th distance to a per-query candidate buffer; a
+// appends only the pairs that come before the query's current k-th (distance, id) to a per-query candidate buffer; a
 // per-query select kernel (bitonic sort by (distance, id)) folds the buffer into the running top-k and tightens
 // the bound.  Base ranges grow geometrically, so a query appends O(k) candidates per pass.
 #include <cuda_runtime.h>
@@ -89,7 +89,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gt_pairs_kernel(const T* __restrict__ base, uint64_t n_base, uint64_t first, uint64_t count,
                                                        uint64_t id_offset, const T* __restrict__ queries, uint32_t nq, uint32_t D,
                                                        const int* __restrict__ base_norm, const int* __restrict__ query_norm,
-                                                       const uint32_t* __restrict__ bound /*[nq] key of the k-th best*/,
+                                                       const unsigned long long* __restrict__ bound /*[nq] key<<32 | id of the k-th best*/,
                                                        unsigned long long* __restrict__ cand /*[nq][kCandCap] key<<32 | id*/,
                                                        uint32_t* __restrict__ cand_n, uint64_t id_base_for_key) {
   __shared__ __align__(16) uint32_t qs[kStepWords][kTile + kPad];
@@ -130,16 +130,17 @@ __global__ void __launch_bounds__(256) gt_pairs_kernel(const T* __restrict__ bas
   for (int i = 0; i < 4; ++i) {
     const uint32_t q = q0 + ty * 4 + i;
     if (q >= nq) continue;
-    const uint32_t bnd = bound[q];
+    const unsigned long long bnd = bound[q];
     const int qn = sizeof(T) == 4 ? 0 : query_norm[q];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint64_t b = b0 + tx * 4 + j;
       if (b >= b_end) continue;
       const uint32_t key = GT<T>::key(acc[i][j], qn, sizeof(T) == 4 ? 0 : base_norm[b]);
-      if (key <= bnd) {
+      const unsigned long long ent = ((unsigned long long)key << 32) | (uint32_t)(b + id_offset - id_base_for_key);
+      if (ent < bnd) {   // strictly before the current k-th (distance, id): ties with larger ids never enter
         const uint32_t pos = atomicAdd(cand_n + q, 1u);
-        if (pos < kCandCap) cand[(size_t)q * kCandCap + pos] = ((unsigned long long)key << 32) | (uint32_t)(b + id_offset - id_base_for_key);
+        if (pos < kCandCap) cand[(size_t)q * kCandCap + pos] = ent;
       }
     }
   }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256) gt_pairs_kernel(const T* __restrict__ bas
 // with the tightened bounds; the entries that did fit are all genuine, repeated ids are dropped here).
 __global__ void __launch_bounds__(1024) gt_select_kernel(unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand_n,
                                                          unsigned long long* __restrict__ topk /*[nq][kMaxK]*/, uint32_t* __restrict__ topk_n,
-                                                         uint32_t k, uint32_t* __restrict__ bound, uint32_t* __restrict__ overflow) {
+                                                         uint32_t k, unsigned long long* __restrict__ bound, uint32_t* __restrict__ overflow) {
   __shared__ unsigned long long s[kSlots];  // 32 KB
   const uint32_t q = blockIdx.x;
   uint32_t n_c = cand_n[q];
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(1024) gt_select_kernel(unsigned long long* __r
     }
     topk_n[q] = u;
     cand_n[q] = 0;
-    if (u == k) bound[q] = (uint32_t)(topk[(size_t)q * kMaxK + k - 1] >> 32);
+    if (u == k) bound[q] = topk[(size_t)q * kMaxK + k - 1];
   }
 }
 
@@ -211,8 +212,8 @@ int gt_run(const T* d_base, uint64_t n, uint32_t D, const T* d_queries, uint32_t
   if (k == 0 || k > kMaxK) { p_err = "k must be in 1..128"; return BANG_E_ARG; }
   if (id_offset + n > 0xFFFFFFFFull) { p_err = "ids exceed 32 bits"; return BANG_E_ARG; }
   int *bn = nullptr, *qn = nullptr;
-  uint32_t *bound = nullptr, *cand_n = nullptr, *topk_n = nullptr, *overflow = nullptr;
-  unsigned long long *cand = nullptr, *topk = nullptr;
+  uint32_t *cand_n = nullptr, *topk_n = nullptr, *overflow = nullptr;
+  unsigned long long *cand = nullptr, *topk = nullptr, *bound = nullptr;
   int rc = BANG_OK;
   auto body = [&]() -> int {
     if (sizeof(T) == 1) {
@@ -221,13 +222,13 @@ int gt_run(const T* d_base, uint64_t n, uint32_t D, const T* d_queries, uint32_t
       norms_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_base, n, D, bn);
       norms_kernel<T><<<(nq + 255) / 256, 256, 0, st>>>(d_queries, nq, D, qn);
     }
-    P_TRY(cudaMalloc(&bound, (size_t)nq * 4));
+    P_TRY(cudaMalloc(&bound, (size_t)nq * 8));
     P_TRY(cudaMalloc(&cand_n, (size_t)nq * 4));
     P_TRY(cudaMalloc(&topk_n, (size_t)nq * 4));
     P_TRY(cudaMalloc(&overflow, 4));
     P_TRY(cudaMalloc(&cand, (size_t)nq * kCandCap * 8));
     P_TRY(cudaMalloc(&topk, (size_t)nq * kMaxK * 8));
-    P_TRY(cudaMemsetAsync(bound, 0xFF, (size_t)nq * 4, st));   // no bound yet: everything is a candidate
+    P_TRY(cudaMemsetAsync(bound, 0xFF, (size_t)nq * 8, st));   // no bound yet: everything is a candidate
     P_TRY(cudaMemsetAsync(cand_n, 0, (size_t)nq * 4, st));
     P_TRY(cudaMemsetAsync(topk_n, 0, (size_t)nq * 4, st));
     // the first pass holds at most kCandCap points (every one of them is a candidate), later passes grow 4x
@@ -245,7 +246,7 @@ int gt_run(const T* d_base, uint64_t n, uint32_t D, const T* d_queries, uint32_t
         P_TRY(cudaMemcpyAsync(&ovf, overflow, 4, cudaMemcpyDeviceToHost, st));
         P_TRY(cudaStreamSynchronize(st));
         if (!ovf) break;
-        if (attempt == 16) { p_err = "ground truth: candidate buffers keep overflowing (thousands of base points at one query's k-th distance?)"; return BANG_E_UNSUPPORTED; }
+        if (attempt == 16) { p_err = "ground truth: candidate buffers keep overflowing (base rows not visited in ascending id order?)"; return BANG_E_UNSUPPORTED; }
       }
       done += cnt;
       pass = std::min<uint64_t>(pass * 4, 1ull << 26);

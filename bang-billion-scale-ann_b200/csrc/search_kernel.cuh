@@ -82,7 +82,7 @@ struct SearchArgs {
   uint32_t n_chunks;
   const float* pivT;        // [D][256]   pivots transposed as the reference does at load (:281-285); stage-1 kernel only
   const float* piv;         // [256][D]   pivots in file order: the shared-memory table of the search kernel
-  uint32_t chunk4;          // uniform chunk size when every chunk spans the same number of dimensions (4 or 3), else 0
+  uint32_t chunk4;          // 4 or 3 when there are exactly 32 chunks of that many dimensions each (selects the CS kernel), else 0
   const float* centroid;    // [D]
   const uint32_t* chunk_off;  // [n_chunks+1]
   uint32_t D;               // dims of the index
@@ -667,9 +667,11 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       if (t == 0 && ka < n) s.n_d[ka] = da;
       if (t == 0 && kb < n) s.n_d[kb] = db;
     }
-  } else if (a.n_chunks <= 32) {
-    const bool full32 = a.n_chunks == 32;
-    for (uint32_t k0 = 0; k0 < n; k0 += 16) {  // 16 candidates' code words in flight
+  } else if (CS > 0) {
+    // uniform chunks and exactly 32 of them (C2 / C4 / C5: D = 128 or 96, 32 bytes per vector): lane t's four chunks
+    // t, t+8, t+16, t+24 are one 32-bit word.  The code words of up to 16 candidates are requested at once; the
+    // table entries are evaluated four candidates (one per 8-lane group) at a time.
+    for (uint32_t k0 = 0; k0 < n; k0 += 16) {
       uint32_t w[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -682,17 +684,16 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       if (__any_sync(kFull, (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x12345678u)) printf("");
       pf.tick(PT_CODEWAIT);
 #endif
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        if (k0 + p * 4 < n) {  // warp-uniform
-          const uint32_t k = k0 + p * 4 + g;
-          const float part = full32 ? adc_group<CS, true>(s, a, w[p], 0, t, 0.0f) : adc_group<CS, false>(s, a, w[p], 0, t, 0.0f);
-          const float sum = tree8(part);
-          if (t == 0 && k < n) s.n_d[k] = sum;
-        }
+#pragma unroll 1
+      for (uint32_t p = 0; p < 4 && k0 + p * 4 < n; ++p) {  // (not unrolled: the kernel's hot loop has to stay inside the instruction cache)
+        const uint32_t k = k0 + p * 4 + g;
+        const uint32_t wp = p == 0 ? w[0] : (p == 1 ? w[1] : (p == 2 ? w[2] : w[3]));
+        const float sum = tree8(adc_group<CS, true>(s, a, wp, 0, t, 0.0f));
+        if (t == 0 && k < n) s.n_d[k] = sum;
       }
     }
   } else {
+    // any chunk layout (uneven chunks, m != 32: the reference's SIFT1B build has 74, SIFT10K 128): 32 chunks per group
     const uint32_t groups = (a.n_chunks + 31) >> 5;
     for (uint32_t k0 = 0; k0 < n; k0 += 4) {
       const uint32_t k = k0 + g;
@@ -990,7 +991,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     auto log_parent = [&](uint32_t node) {
       if (lane == 0) {
         if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
-        if (a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = node;
+        if (MODE == kExact && a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = node;  // (index builder)
       }
       if (ncand < a.cand_cap) ++ncand;
     };
@@ -1063,8 +1064,11 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
           if (nb > 0 && (fu == kNone || b.d <= s.w_d[fu])) { have = true; from_new = true; parent = b.id; }
           else if (fu != kNone) { have = true; parent = s.w_id[fu]; }
         }
-        if (!have) {  // nothing unvisited and nothing admitted: the merge would be a no-op, except for a first hop that
-          if (first && nb > 0) ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, true, kNone, &pos0);  // found only the medoid
+        if (!have) {  // nothing unvisited and nothing admitted: the merge would be a no-op — except on a first hop whose
+          if (first && nb > 0) {  // sorted list starts with the medoid and offers nothing else: the worklist is [medoid, visited]
+            if (lane == 0) { s.w_id[0] = a.medoid; s.w_d[0] = b.med_d; s.w_v[0] = 1; }
+            ws = 1;
+          }
           break;
         }
         uint32_t scan_from = fu == kNone ? ws : fu;
@@ -1103,7 +1107,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     if (lane == 0 && a.st_phase) for (int i = 0; i < PT_COUNT; ++i) a.st_phase[(size_t)q * PT_COUNT + i] = pf.acc[i];
 #endif
     if (lane == 0) {
-      if (a.dump_ids) {
+      if (MODE == kExact && a.dump_ids) {
         a.dump_ids[(size_t)q * a.dump_stride] = a.medoid;
         a.dump_n[q] = min(ncand, a.dump_stride);
       }

@@ -5,9 +5,9 @@ mkdir -p gpurun_out
 echo "== GPU suite"
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -15
 echo "== bench --impl reference (default workload)"
-/usr/bin/time -v timeout 1500 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2e_ref.json 2> gpurun_out/r2e_ref.err
-grep -E "Elapsed|Maximum resident" gpurun_out/r2e_ref.err; grep "\[bench\]" gpurun_out/r2e_ref.err | cut -c1-400; cut -c1-900 gpurun_out/r2e_ref.json
+S=$SECONDS; timeout 1500 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2e_ref.json 2> gpurun_out/r2e_ref.err
+echo "wall $((SECONDS-S)) s"; grep "\[bench\]" gpurun_out/r2e_ref.err | cut -c1-400; cut -c1-900 gpurun_out/r2e_ref.json
 echo "== bench (default workload)"
-/usr/bin/time -v timeout 1500 python bench.py --steps 5 --warmup 3 > gpurun_out/r2e_b200.json 2> gpurun_out/r2e_b200.err
-grep -E "Elapsed|Maximum resident" gpurun_out/r2e_b200.err; grep "\[bench" gpurun_out/r2e_b200.err | cut -c1-300; cut -c1-3000 gpurun_out/r2e_b200.json
+S=$SECONDS; timeout 1500 python bench.py --steps 5 --warmup 3 > gpurun_out/r2e_b200.json 2> gpurun_out/r2e_b200.err
+echo "wall $((SECONDS-S)) s"; tail -3 gpurun_out/r2e_b200.err | cut -c1-300; grep "\[bench" gpurun_out/r2e_b200.err | cut -c1-300; cut -c1-3000 gpurun_out/r2e_b200.json
 df -h /dev/shm | tail -1
