@@ -2,6 +2,7 @@
 
 Artefacts (all git-ignored, all travel to the GPU box with the gpurun snapshot):
   bang-billion-scale-ann_b200/libbang_b200.so      CUDA kernels + C ABI (sm_100a)         <- the product
+  bang-billion-scale-ann_b200/libbang_b200_prof.so the same with per-phase clocks (BANG_B200_TIMERS=2 only)
   bang-billion-scale-ann_b200/libbang_fixture.so   host-only fixture builder (Vamana)     <- tooling
   bang-billion-scale-ann_b200/bang_search          CLI driver with the reference's argv   <- product
   oracle/libbang_oracle.so                         CPU restatement (test infrastructure)
@@ -104,6 +105,22 @@ def build_variant(name: str, defines: list[str], verbose_ptxas: bool = False) ->
     return out
 
 
+LIB_PROF = os.path.join(PKG_DIR, "libbang_b200_prof.so")
+
+
+def build_prof(force: bool = False) -> str:
+    """libbang_b200_prof.so: the same sources with -DBANG_PHASE_TIMERS (per-phase SM clocks inside the fused kernel).
+    The C++ class loads it instead of the product kernels when BANG_B200_TIMERS=2 and prints the reference's `_TIMERS`
+    breakdown (bang_search.cu:1028-1051); never loaded otherwise."""
+    deps = _srcs(CSRC) + _srcs(INCLUDE)
+    if not force and _newer(LIB_PROF, deps):
+        return LIB_PROF
+    if not os.path.exists(NVCC):
+        return LIB_PROF
+    _compile_cuda_lib(LIB_PROF, ["BANG_PHASE_TIMERS"], False)
+    return LIB_PROF
+
+
 def build_cli(force: bool = False) -> str:
     src = os.path.join(CSRC, "bang_search_main.cpp")
     if not force and _newer(CLI, [src, LIB_CUDA] + _srcs(INCLUDE)):
@@ -172,6 +189,7 @@ def build_all(force: bool = False) -> None:
     build_preprocess(force)
     build_oracle(force)
     build_cuda(force)
+    build_prof(force)
     build_cli(force)
     build_cli_inmem(force)
     build_reference(force)

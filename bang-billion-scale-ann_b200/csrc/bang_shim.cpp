@@ -1,16 +1,75 @@
 // bang_shim.cpp — `BANGSearch<T>` (include/bang.h) and the reference's C entry points over the C ABI.
 // Replaces the API shims of the reference (BANG_Base/bang_search.cu:70-135 and the `#if 0` block at
 // :1787-1806); each method is a one-line forward to bang_b200_*.
+#include <dlfcn.h>
+
+#include <algorithm>
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "bang.h"
 #include "bang_b200.h"
 
+extern "C" int bang_b200_debug_phase_clocks(bang_handle_t h, long long* out);
+
 namespace {
+
+// The C ABI the class forwards to: this library's own entry points, or — with BANG_B200_TIMERS=2 — those of
+// libbang_b200_prof.so (the same sources compiled with -DBANG_PHASE_TIMERS: every query warp keeps SM-clock totals per
+// phase of the fused kernel), from which the reference's `_TIMERS` breakdown (bang_search.cu:1028-1051) is printed.
+struct Abi {
+  decltype(&bang_b200_create) create = bang_b200_create;
+  decltype(&bang_b200_destroy) destroy = bang_b200_destroy;
+  decltype(&bang_b200_load) load = bang_b200_load;
+  decltype(&bang_b200_set_searchparams) set_searchparams = bang_b200_set_searchparams;
+  decltype(&bang_b200_alloc) alloc = bang_b200_alloc;
+  decltype(&bang_b200_init) init = bang_b200_init;
+  decltype(&bang_b200_query) query = bang_b200_query;
+  decltype(&bang_b200_free) free_ = bang_b200_free;
+  decltype(&bang_b200_unload) unload = bang_b200_unload;
+  decltype(&bang_b200_last_error) last_error = bang_b200_last_error;
+  decltype(&bang_b200_last_timing) last_timing = bang_b200_last_timing;
+  decltype(&bang_b200_last_stats) last_stats = bang_b200_last_stats;
+  decltype(&bang_b200_debug_phase_clocks) phase_clocks = nullptr;
+  int timers = 0;   // BANG_B200_TIMERS: 0 off, 1 totals, 2 per-phase breakdown (needs the phase-clock build)
+};
+
+const Abi& abi() {
+  static const Abi a = [] {
+    Abi t;
+    const char* e = getenv("BANG_B200_TIMERS");
+    t.timers = e ? (atoi(e) >= 2 ? 2 : 1) : 0;
+    if (t.timers == 2) {
+      Dl_info info;
+      std::string path;
+      if (dladdr(reinterpret_cast<void*>(&bang_b200_create), &info) && info.dli_fname) {
+        path = info.dli_fname;
+        const size_t slash = path.rfind('/');
+        path = (slash == std::string::npos ? std::string() : path.substr(0, slash + 1)) + "libbang_b200_prof.so";
+      }
+      void* lib = path.empty() ? nullptr : dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (!lib) {
+        fprintf(stderr, "bang_b200: BANG_B200_TIMERS=2 needs %s (python -c 'from bang_b200 import build; build.build_prof()'); printing totals only\n",
+                path.empty() ? "libbang_b200_prof.so" : path.c_str());
+        t.timers = 1;
+        return t;
+      }
+#define BANG_SYM(field, name) t.field = reinterpret_cast<decltype(t.field)>(dlsym(lib, name))
+      BANG_SYM(create, "bang_b200_create"); BANG_SYM(destroy, "bang_b200_destroy"); BANG_SYM(load, "bang_b200_load");
+      BANG_SYM(set_searchparams, "bang_b200_set_searchparams"); BANG_SYM(alloc, "bang_b200_alloc"); BANG_SYM(init, "bang_b200_init");
+      BANG_SYM(query, "bang_b200_query"); BANG_SYM(free_, "bang_b200_free"); BANG_SYM(unload, "bang_b200_unload");
+      BANG_SYM(last_error, "bang_b200_last_error"); BANG_SYM(last_timing, "bang_b200_last_timing"); BANG_SYM(last_stats, "bang_b200_last_stats");
+      BANG_SYM(phase_clocks, "bang_b200_debug_phase_clocks");
+#undef BANG_SYM
+    }
+    return t;
+  }();
+  return a;
+}
 
 template <typename T> struct dtype_of;
 template <> struct dtype_of<float> { static constexpr bang_dtype_t v = BANG_DT_FLOAT; };
@@ -34,7 +93,7 @@ bang_mode_t mode_from_env() {
 
 void note(Impl* p, int rc, const char* what) {
   if (rc == BANG_OK) return;
-  p->err = std::string(what) + ": " + bang_b200_last_error();
+  p->err = std::string(what) + ": " + abi().last_error();
   fprintf(stderr, "bang_b200 error in %s\n", p->err.c_str());
 }
 
@@ -51,7 +110,7 @@ BANGSearch<T>::BANGSearch() {
 template <typename T>
 BANGSearch<T>::~BANGSearch() {
   Impl* p = static_cast<Impl*>(m_pImpl);
-  if (p->h) bang_b200_destroy(p->h);
+  if (p->h) abi().destroy(p->h);
   delete p;
 }
 
@@ -67,10 +126,10 @@ template <typename T>
 bool BANGSearch<T>::bang_load(char* prefix) {
   Impl* p = static_cast<Impl*>(m_pImpl);
   if (!p->h) {
-    int rc = bang_b200_create(&p->h, p->dtype, p->mode, -1);
+    int rc = abi().create(&p->h, p->dtype, p->mode, -1);
     if (rc != BANG_OK) { note(p, rc, "bang_load"); p->h = nullptr; return false; }
   }
-  int rc = bang_b200_load(p->h, prefix);
+  int rc = abi().load(p->h, prefix);
   note(p, rc, "bang_load");
   return rc == BANG_OK;
 }
@@ -78,19 +137,19 @@ bool BANGSearch<T>::bang_load(char* prefix) {
 template <typename T>
 void BANGSearch<T>::bang_alloc(int numQueries) {
   Impl* p = static_cast<Impl*>(m_pImpl);
-  note(p, p->h ? bang_b200_alloc(p->h, numQueries) : BANG_E_STATE, "bang_alloc");
+  note(p, p->h ? abi().alloc(p->h, numQueries) : BANG_E_STATE, "bang_alloc");
 }
 
 template <typename T>
 void BANGSearch<T>::bang_init(int numQueries) {
   Impl* p = static_cast<Impl*>(m_pImpl);
-  note(p, p->h ? bang_b200_init(p->h, numQueries) : BANG_E_STATE, "bang_init");
+  note(p, p->h ? abi().init(p->h, numQueries) : BANG_E_STATE, "bang_init");
 }
 
 template <typename T>
 void BANGSearch<T>::bang_set_searchparams(int recall, int worklist_length, DistFunc nDistFunc) {
   Impl* p = static_cast<Impl*>(m_pImpl);
-  note(p, p->h ? bang_b200_set_searchparams(p->h, recall, worklist_length, static_cast<bang_distfn_t>(nDistFunc)) : BANG_E_STATE,
+  note(p, p->h ? abi().set_searchparams(p->h, recall, worklist_length, static_cast<bang_distfn_t>(nDistFunc)) : BANG_E_STATE,
        "bang_set_searchparams");
 }
 
@@ -98,37 +157,67 @@ template <typename T>
 void BANGSearch<T>::bang_query(T* query_array, int num_queries, result_ann_t* nearestNeighbours, float* nearestNeighbours_dist) {
   Impl* p = static_cast<Impl*>(m_pImpl);
   static_assert(sizeof(result_ann_t) == sizeof(uint64_t), "result_ann_t is 64-bit");
-  static const bool timers = getenv("BANG_B200_TIMERS") != nullptr;  // run-time stand-in for the reference's -D_TIMERS build
+  const int timers = abi().timers;  // run-time stand-in for the reference's -D_TIMERS build
   const auto t0 = std::chrono::steady_clock::now();
-  note(p, p->h ? bang_b200_query(p->h, query_array, num_queries, reinterpret_cast<uint64_t*>(nearestNeighbours), nearestNeighbours_dist)
+  note(p, p->h ? abi().query(p->h, query_array, num_queries, reinterpret_cast<uint64_t*>(nearestNeighbours), nearestNeighbours_dist)
                : BANG_E_STATE,
        "bang_query");
   if (timers && p->h) {
-    // The reference prints one line per kernel family (bang_search.cu:1030-1050); here stages (1)-(6) are one fused
-    // launch, so the breakdown is: that launch on the device, and what is left of the wall clock (copies + launch).
     const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     bang_b200_timing_t tm;
-    if (bang_b200_last_timing(p->h, &tm) == BANG_OK) {
+    if (abi().last_timing(p->h, &tm) != BANG_OK) return;
+    std::vector<long long> ph;
+    if (timers == 2 && abi().phase_clocks) {
+      ph.resize((size_t)num_queries * 16);
+      if (abi().phase_clocks(p->h, ph.data()) != BANG_OK) ph.clear();
+    }
+    if (!ph.empty()) {
+      // The reference times one kernel family per bucket (bang_search.cu:1030-1050).  Here all of them are one launch:
+      // every query warp accumulates SM clocks per phase of its own search; a bucket below is the fused kernel's device
+      // time multiplied by that phase's share of the summed clocks.  Slots: 0 setup, 1 adjacency wait, 2 hashes, 3 filter
+      // loads + tests, 4 reservations + compaction, 5 code wait, 6 table entries + sums, 7 neighbour scan, 8 parent decision,
+      // 9 sort + merge, 10 first-unvisited scan, 11 re-rank, 13 hops.
+      double c[16] = {0};
+      long long max_hops = 0;
+      for (int q = 0; q < num_queries; ++q) {
+        for (int i = 0; i < 12; ++i) c[i] += (double)ph[(size_t)q * 16 + i];
+        max_hops = std::max(max_hops, ph[(size_t)q * 16 + 13]);
+      }
+      double tot = 0;
+      for (int i = 0; i < 12; ++i) tot += c[i];
+      const double f = tot > 0 ? tm.kernel_ms / tot : 0.0;
+      printf("STATS:\nTotal Search iterations = %lld\n", max_hops);
+      printf("(1) PD Dist Table Construction = %.3f ms\n", c[0] * f);   // query residual only: table entries are evaluated on demand, inside (2)
+      printf("(2) Distance Computations = %.3f ms\n", (c[5] + c[6]) * f);
+      printf("(3) Sort and Merge = %.3f ms\n", c[9] * f);
+      printf("(4) total neighbor_filtering_time = %.3f ms\n", (c[2] + c[3] + c[4]) * f);
+      printf("(5) Pre-fetch time = %.3f ms\n", (c[7] + c[8] + c[10]) * f);     // parent selection (compute_parent1/2)
+      printf("(6) Time elapsed in L2 Dist computation (GPU)= %.3f ms\n", c[11] * f);
+      printf("(7) total transfer_time (CPU <--> GPU) = %.3f ms\n", wall - tm.kernel_ms);
+      printf("(8) total neigbbour seek time = %.3f ms\n", c[1] * f);               // waiting for the expanded node's adjacency row (HBM / NVLink)
+      printf("Total time from timers = (1) + (2) + (3) + (4) + (5) + (6) + (8) = %.3f ms  (phase-clock build: ~7 %% slower than the product kernel)\n", tm.kernel_ms);
+    } else {
+      // stages (1)-(6) are one fused launch: that launch on the device, and what is left of the wall clock (copies + launch)
       printf("(1)-(6) fused search kernel (%u launch, grid %u x %u threads, %u B smem) = %.3f ms\n", tm.launches, tm.grid, tm.block,
              tm.smem_bytes, tm.kernel_ms);
       printf("(7) total transfer_time + launch (CPU <--> GPU: %llu B in, %llu B out) = %.3f ms\n", (unsigned long long)tm.h2d_bytes,
              (unsigned long long)tm.d2h_bytes, wall - tm.kernel_ms);
-      printf("Wall Clock Time = %.3f\nThroughput = %.2f QPS\nThroughput (Exclude Mem Transfers) = %.2f QPS\n", wall,
-             num_queries * 1000.0 / wall, num_queries * 1000.0 / tm.kernel_ms);
     }
+    printf("Wall Clock Time = %.3f\nThroughput = %.2f QPS\nThroughput (Exclude Mem Transfers) = %.2f QPS\n", wall,
+           num_queries * 1000.0 / wall, num_queries * 1000.0 / tm.kernel_ms);
   }
 }
 
 template <typename T>
 void BANGSearch<T>::bang_free() {
   Impl* p = static_cast<Impl*>(m_pImpl);
-  if (p->h) note(p, bang_b200_free(p->h), "bang_free");
+  if (p->h) note(p, abi().free_(p->h), "bang_free");
 }
 
 template <typename T>
 void BANGSearch<T>::bang_unload() {
   Impl* p = static_cast<Impl*>(m_pImpl);
-  if (p->h) note(p, bang_b200_unload(p->h), "bang_unload");
+  if (p->h) note(p, abi().unload(p->h), "bang_unload");
 }
 
 template <typename T>

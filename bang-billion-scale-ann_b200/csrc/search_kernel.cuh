@@ -40,6 +40,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef BANG_PHASE_TIMERS
+#include <cstdio>  // (the phase-clock build pins loads in place with never-taken printf branches)
+#endif
 
 
 namespace bang {
@@ -204,11 +207,7 @@ __device__ __forceinline__ uint4 ld_nc_u4(const void* p, uint64_t pol) {
 }
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 r;
-#ifdef BANG_PLAIN_ROW_LOADS  // experimental: graph rows (possibly peer memory) through the ordinary coherent load path
-  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-#else
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-#endif
   return r;
 }
 __device__ __forceinline__ uint32_t ld_nc_u32(const void* p, uint64_t pol) {
@@ -247,7 +246,7 @@ __device__ __forceinline__ bool vis_test(const uint32_t* vbm, uint2 blk, VisAddr
 }
 // set a slot (not currently set), in two steps so that nothing waits for the atomic's round trip:
 // vis_reserve bumps the block's count byte with one L2 atomic and returns the old count word; vis_commit, called
-// once the hop's code loads are in flight, stores the offset byte into the reserved position.  Reservations
+// after the distance computations of the hop, stores the offset byte into the reserved position.  Reservations
 // 7 and up belong to the spill bitmap (vis_spill_*): the one lane that drew number 7 clears the block's bitmap,
 // then, after a warp barrier, every lane with a number >= 7 sets its bit.
 __device__ __forceinline__ uint32_t vis_reserve(uint8_t* vis, VisAddr a) {
@@ -498,13 +497,8 @@ __device__ __forceinline__ void load_query_residual(const SearchArgs& a, uint32_
 __device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream) {
   uint2 r;
   const uint8_t* p = row_ptr(a, node) + 8 * (threadIdx.x & 31);
-#ifdef BANG_PLAIN_ROW_LOADS
-  (void)pol_stream;
-  asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-#else
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
                : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_stream));
-#endif
   return r;
 }
 
@@ -649,9 +643,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   }
   __syncwarp();
   pf.tick(PT_COMPACT);
-  // The reserved filter bytes are stored once the first code loads of the hop are in flight: the atomics were
-  // issued before the compaction and have returned by then, and nothing of the filter phase stays live across
-  // the distance computations.
+  // The reserved filter bytes are stored after the distance computations of the hop: the atomics that hand out the
+  // byte positions have long returned by then, so nothing waits for their round trip.
   FilterIns fi;
   fi.a[0] = a01; fi.a[1] = a02; fi.a[2] = a11; fi.a[3] = a12;
   fi.r[0] = r01; fi.r[1] = r02; fi.r[2] = r11; fi.r[3] = r12;
@@ -679,7 +672,6 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
         w[p] = 0;
         if (k < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[k] * a.code_stride + 4 * t, s.pol_stream);
       }
-      if (k0 == 0) commit_filter(vis, vbm, fi);
 #ifdef BANG_PHASE_TIMERS
       if (__any_sync(kFull, (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x12345678u)) printf("");
       pf.tick(PT_CODEWAIT);
@@ -702,7 +694,6 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       for (uint32_t gg = 0; gg < groups; gg += 2) {
         const uint32_t wa = ld_nc_u32(row + gg * 32, s.pol_stream);
         const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32, s.pol_stream) : 0u;
-        if (k0 == 0 && gg == 0) commit_filter(vis, vbm, fi);
         sum = adc_group<CS, false>(s, a, wa, gg * 32, t, sum);
         sum = adc_group<CS, false>(s, a, wb, (gg + 1) * 32, t, sum);
       }
@@ -710,7 +701,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       if (t == 0 && k < n) s.n_d[k] = sum;
     }
   }
-  if (MODE == kExact || n == 0) commit_filter(vis, vbm, fi);
+  commit_filter(vis, vbm, fi);
   __syncwarp();
   pf.tick(PT_LUT);
   return n;
@@ -1007,18 +998,24 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       float pend_maxd = 0.0f;
       while (have || pend_n > 0) {
         if (have) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
+        pf.tick(PT_DECIDE);
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
           ws = merge_worklist(a, s, pend_n, pend_nb, pend_below, pend_maxd, ws, iter == 1, mark, &pos0);
           scan_from = min(scan_from, pos0);
+          pf.count(PT_MERGES);
         }
+        pf.tick(PT_MERGE);
         fu = scan_unvisited(s, scan_from, ws);
         scan_from = fu == kNone ? ws : fu;
+        pf.tick(PT_UNVIS);
+        pf.count(PT_HOPS);
         n = 0;
         if (have) n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, pf);
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
         b = scan_neighbours(s, n, a.medoid, true, maxd);
+        pf.tick(PT_SCAN);
         const bool hasx = b.id != kNone;
         have = false;
         if (fu != kNone) {
@@ -1036,7 +1033,9 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         if (iter == a.max_iter - 1) break;
       }
       write_stats(a, s, q);
+      pf.tick(PT_DECIDE);
       rerank_and_write<T>(a, s, q, ncand);
+      pf.tick(PT_RERANK);
     } else {
       // ---- BANG_Inmemory / BANG_Exactdistance (A.2', A.2''): { expand(parent) ; merge ; first unvisited } ----
       // The first unvisited entry after the merge is decided before it: the closest new entry if it is

@@ -222,6 +222,36 @@ def test_cli_driver_reports_reference_table(fx_u8):
     assert abs(float(lines[-1].split("\t")[3]) - want) < 0.01
 
 
+@pytest.mark.parametrize("mode", ["base", "inmemory"])
+def test_timers_breakdown_like_the_reference(fx_u8, mode):
+    """BANG_B200_TIMERS=2: the driver prints the reference's `_TIMERS` table (bang_search.cu:1028-1051) from the phase
+    clocks of libbang_b200_prof.so; the eight buckets add up to the fused kernel's device time and the answers do not change."""
+    fx = fx_u8
+    exe = build.build_cli()
+    build.build_prof()
+    out = {}
+    for timers in ("2", None):
+        env = dict(os.environ, BANG_B200_MODE=mode)
+        env.pop("BANG_B200_TIMERS", None)
+        if timers:
+            env["BANG_B200_TIMERS"] = timers
+        r = subprocess.run([exe, fx.prefix, fx.paths.query, fx.paths.truth, str(len(fx.queries)), "10", "uint8", "l2", "40"],
+                           capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr
+        out[timers] = r.stdout
+    txt = out["2"]
+    assert txt.count("STATS:") == 5 and "Total Search iterations" in txt
+    import re
+    blk = txt.split("STATS:")[-1]
+    vals = {int(m.group(1)): float(m.group(2)) for m in re.finditer(r"^\((\d)\) [^=]*= ([0-9.]+) ms", blk, re.M)}
+    assert sorted(vals) == [1, 2, 3, 4, 5, 6, 7, 8]
+    total = float(re.search(r"Total time from timers[^=]*=[^=]*= ([0-9.]+) ms", blk).group(1))
+    assert abs(sum(vals[i] for i in (1, 2, 3, 4, 5, 6, 8)) - total) < 0.02 * total + 0.01
+    assert vals[2] > 0 and vals[4] > 0 and vals[6] > 0
+    rows = lambda t: [l.split("\t")[3] for l in t.splitlines() if l.startswith("40\t")]
+    assert rows(out["2"]) == rows(out[None])      # same recall column with and without the clocks
+
+
 REF_DRIVER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_driver")
 
 
