@@ -17,6 +17,7 @@ the row.  PQ codes are encoded by the chunk's owner and broadcast (they are repl
 """
 from __future__ import annotations
 
+import sys
 import time
 
 import numpy as np
@@ -31,7 +32,7 @@ SIGMA_U8 = 24.0
 
 def log(rank, *a):
     if rank == 0:
-        print("[c5]", *a, flush=True)
+        print("[c5]", *a, file=sys.stderr, flush=True)   # (stdout belongs to the caller: bench.py prints one JSON line there)
 
 
 def mixture_centers(n_clusters: int, d: int, device) -> torch.Tensor:

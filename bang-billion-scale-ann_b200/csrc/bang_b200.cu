@@ -656,9 +656,10 @@ static int alloc_impl(bang_b200_ctx* c, int Q) {
   int max_optin = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   CUDA_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
-  // Resident queries per SM: as many query warps as shared memory and the register file allow (PQ modes: up to 32,
-  // one CTA per SM around one pivot table; Exactdistance: 2 CTAs of 16).  BANG_B200_WARPS_PER_SM overrides.
-  int max_warps = 32;
+  // Resident queries per SM.  PQ modes: one CTA per SM around one pivot table with up to 24 query warps (80
+  // registers each) — 16 (128 registers) and 32 (64 registers) are within 2-7 % on C2 / DEEP shapes, 24 is the best
+  // of the three on both; Exactdistance: 2 CTAs of 16.  BANG_B200_WARPS_PER_SM overrides (up to 32).
+  int max_warps = c->mode == BANG_MODE_EXACTDISTANCE ? 32 : 24;   // measured: profiles/r2_concurrency.md
   if (const char* e = getenv("BANG_B200_WARPS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) max_warps = v; }
   if (const char* e = getenv("BANG_B200_CODE_PREFETCH")) c->code_prefetch = atoi(e) != 0;
   // A pivot table that does not fit next to one query's state (256 x D floats: D above ~215) stays in global memory
