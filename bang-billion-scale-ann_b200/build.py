@@ -80,7 +80,9 @@ def _compile_cuda_lib(out: str, defines: list[str], verbose_ptxas: bool) -> None
         jobs.append([NVCC, *common, "-c", os.path.join(CSRC, src), "-o", obj])
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
         list(ex.map(_run, jobs))
-    _run([NVCC, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", out, *objs, "-lgomp"])
+    # -Bsymbolic: references inside the library bind to its own definitions, so that libbang_b200_prof.so can be
+    # dlopen'ed next to libbang_b200.so (same symbol names) and still launch its own kernels
+    _run([NVCC, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-Bsymbolic", "-o", out, *objs, "-lgomp"])
     shutil.rmtree(objdir, ignore_errors=True)
 
 

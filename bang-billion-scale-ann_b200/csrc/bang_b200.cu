@@ -157,6 +157,7 @@ struct bang_b200_ctx {
   unsigned long long* d_bad = nullptr;  // row validation counters: degree > R, id >= N, duplicate id (see validate_row)
   bool piv_global = false;              // the pivot table does not fit in shared memory: read it from global/L2
   bool code_prefetch = true;            // speculative L2 prefetch of every neighbour's PQ code row (BANG_B200_CODE_PREFETCH)
+  bool row_prefetch = false;            // L2 prefetch of the likely next node's row at the start of each hop (BANG_B200_ROW_PREFETCH)
   // params
   int k = 0, L = 0, distfn = BANG_DIST_L2, dists_layout = BANG_DISTS_RANK_MAJOR;
   // per-alloc scratch
@@ -204,10 +205,11 @@ static table_fn_t pick_table_kernel(int dtype) {
 }
 static LaunchGeom geometry_for(const bang_b200_ctx* c, uint32_t L, uint32_t cand_cap, size_t optin, size_t per_sm, int max_warps,
                                bool piv_global) {
+  const uint32_t piv_row = pivot_row_floats(c->D, piv_global ? 0 : c->chunk4);
   switch (c->dtype) {
-    case BANG_DT_FLOAT: return launch_geometry<float>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
-    case BANG_DT_INT8: return launch_geometry<int8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
-    default: return launch_geometry<uint8_t>(c->mode, c->D, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
+    case BANG_DT_FLOAT: return launch_geometry<float>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
+    case BANG_DT_INT8: return launch_geometry<int8_t>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
+    default: return launch_geometry<uint8_t>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
   }
 }
 static uint32_t max_iter_for(int mode, int L) {
@@ -266,20 +268,30 @@ static int upload_pq(bang_b200_ctx* c, const PQHost& pq) {
   if (pq.chunk_off.back() != D) return set_err(BANG_E_FORMAT, "chunk offsets do not end at D");
   for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
     if (pq.chunk_off[i] > pq.chunk_off[i + 1]) return set_err(BANG_E_FORMAT, "chunk offsets not monotone");
-  // 32 chunks of one size (4: SIFT 128/32; 3: DEEP 96/32) select a compile-time ADC path; everything else the general one
+  // 32 chunks of one size <= 4 (4: SIFT 128/32; 3: DEEP 96/32) select the CS = 4 kernels, whose pivot table has every
+  // chunk zero-padded to 4 dimensions ([256][32][4], one 16-byte load per table entry); everything else the general kernel
   c->chunk4 = pq.chunk_off.size() > 1 ? pq.chunk_off[1] - pq.chunk_off[0] : 0;
   for (size_t i = 0; i + 1 < pq.chunk_off.size(); ++i)
     if (pq.chunk_off[i + 1] - pq.chunk_off[i] != c->chunk4) c->chunk4 = 0;
-  if ((c->chunk4 != 4 && c->chunk4 != 3) || c->n_chunks != 32) c->chunk4 = 0;  // the CS kernels assume one full 32-chunk group
-  CUDA_TRY(cudaMalloc(&c->d_piv, pq.pivots.size() * 4));
-  CUDA_TRY(cudaMemcpy(c->d_piv, pq.pivots.data(), pq.pivots.size() * 4, cudaMemcpyHostToDevice));
+  if (c->chunk4 < 1 || c->chunk4 > 4 || c->n_chunks != 32) c->chunk4 = 0;  // the CS = 4 kernels assume one full 32-chunk group
+  std::vector<float> padded;
+  const std::vector<float>* table = &pq.pivots;
+  if (c->chunk4) {
+    padded.assign((size_t)256 * 128, 0.0f);
+    for (uint32_t row = 0; row < 256; ++row)
+      for (uint32_t ch = 0; ch < 32; ++ch)
+        for (uint32_t e = 0; e < c->chunk4; ++e) padded[(size_t)row * 128 + ch * 4 + e] = pq.pivots[(size_t)row * D + ch * c->chunk4 + e];
+    table = &padded;
+  }
+  CUDA_TRY(cudaMalloc(&c->d_piv, table->size() * 4));
+  CUDA_TRY(cudaMemcpy(c->d_piv, table->data(), table->size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&c->d_pivT, pivT.size() * 4));
   CUDA_TRY(cudaMalloc(&c->d_centroid, (size_t)D * 4));
   CUDA_TRY(cudaMalloc(&c->d_chunk_off, pq.chunk_off.size() * 4));
   CUDA_TRY(cudaMemcpy(c->d_pivT, pivT.data(), pivT.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->d_centroid, pq.centroid.data(), (size_t)D * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->d_chunk_off, pq.chunk_off.data(), pq.chunk_off.size() * 4, cudaMemcpyHostToDevice));
-  c->device_bytes += 2 * pivT.size() * 4 + (size_t)D * 4 + pq.chunk_off.size() * 4;
+  c->device_bytes += (pivT.size() + table->size()) * 4 + (size_t)D * 4 + pq.chunk_off.size() * 4;
   return BANG_OK;
 }
 
@@ -384,6 +396,7 @@ static int load_codes(bang_b200_ctx* c, const std::string& path) {
 static int check_common(bang_b200_ctx* c) {
   if (c->R != (uint32_t)kMaxR) return set_err(BANG_E_UNSUPPORTED, "graph degree bound must be 64 (MAX_R, bang_search.cu:35,190)");
   if (c->N == 0 || c->N > 0xFFFFFFFEull) return set_err(BANG_E_FORMAT, "bad dataset size");
+  if (c->N > 0x80000000ull) return set_err(BANG_E_UNSUPPORTED, "more than 2^31 points (the worklist keeps its visited flag in the top bit of the id)");
   if (c->medoid >= c->N) return set_err(BANG_E_FORMAT, "medoid out of range");
   if (c->entry_len != (uint64_t)c->D * elem_size(c->dtype) + 4 + 4ull * c->R)
     return set_err(BANG_E_FORMAT, "index entry length does not match D*sizeof(T)+4+4R (wrong element type?)");
@@ -662,6 +675,7 @@ static int alloc_impl(bang_b200_ctx* c, int Q) {
   int max_warps = c->mode == BANG_MODE_EXACTDISTANCE ? 32 : 24;   // measured: profiles/r2_concurrency.md
   if (const char* e = getenv("BANG_B200_WARPS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) max_warps = v; }
   if (const char* e = getenv("BANG_B200_CODE_PREFETCH")) c->code_prefetch = atoi(e) != 0;
+  if (const char* e = getenv("BANG_B200_ROW_PREFETCH")) c->row_prefetch = atoi(e) != 0;
   // A pivot table that does not fit next to one query's state (256 x D floats: D above ~215) stays in global memory
   // (L2-resident, read with plain loads by the generic-chunk kernel) instead of being refused.
   c->piv_global = false;
@@ -673,7 +687,7 @@ static int alloc_impl(bang_b200_ctx* c, int Q) {
   if (g.warps_per_cta < 1)
     return set_err(BANG_E_UNSUPPORTED, "one query's state (D = " + std::to_string(c->D) + ", L = " + std::to_string(c->L) + ") does not fit in " +
                                            std::to_string(max_optin) + " B of shared memory");
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->piv_global ? 0 : c->chunk4, g.warps_per_cta);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, (c->piv_global || !c->chunk4) ? 0 : 4, g.warps_per_cta);
   c->smem = g.smem;
   c->warps_per_cta = g.warps_per_cta;
   CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
@@ -770,6 +784,7 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   a->n_chunks = c->n_chunks;
   a->pivT = c->d_pivT;
   a->piv = c->d_piv;
+  a->piv_row = pivot_row_floats(c->D, c->piv_global ? 0 : c->chunk4);
   a->chunk4 = c->chunk4;
   a->centroid = c->d_centroid;
   a->chunk_off = c->d_chunk_off;
@@ -789,6 +804,7 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   a->cand_log = c->d_candlog;
   a->piv_global = c->piv_global ? 1u : 0u;
   a->code_prefetch = c->code_prefetch ? 1u : 0u;
+  a->row_prefetch = c->row_prefetch ? 1u : 0u;
   a->stop_on_empty_hop = c->mode == BANG_MODE_EXACTDISTANCE ? 1u : 0u;  // BANG_Exactdistance/parANN.cu:1593-1671 as built
   a->counter = c->d_counter;
   a->st_hops = c->d_hops;
@@ -804,7 +820,7 @@ static int launch_search(bang_b200_ctx* c, const void* d_queries, int Q, uint64_
   if (c->busy) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_busy, 0));
   CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4, st));
   const int grid = std::min((Q + c->warps_per_cta - 1) / c->warps_per_cta, c->grid);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, c->piv_global ? 0 : c->chunk4, c->warps_per_cta);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, (c->piv_global || !c->chunk4) ? 0 : 4, c->warps_per_cta);
   fn<<<grid, c->warps_per_cta * 32, c->smem, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c->ev_busy, st));

@@ -51,7 +51,8 @@ const Abi& abi() {
         const size_t slash = path.rfind('/');
         path = (slash == std::string::npos ? std::string() : path.substr(0, slash + 1)) + "libbang_b200_prof.so";
       }
-      void* lib = path.empty() ? nullptr : dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+      void* lib = path.empty() ? nullptr : dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND);  // (DEEPBIND: the copy's own
+      // kernels and helpers, not the same-named ones of the product library this process already has in its global scope)
       if (!lib) {
         fprintf(stderr, "bang_b200: BANG_B200_TIMERS=2 needs %s (python -c 'from bang_b200 import build; build.build_prof()'); printing totals only\n",
                 path.empty() ? "libbang_b200_prof.so" : path.c_str());

@@ -1,5 +1,5 @@
 // search_inst.cuh — the fused search kernel is instantiated once per element type, each in its own translation unit
-// (search_inst_u8.cu / _i8.cu / _f32.cu: 19 kernels apiece, compiled in parallel by build.py); the host code picks
+// (search_inst_u8.cu / _i8.cu / _f32.cu: 13 kernels apiece, compiled in parallel by build.py); the host code picks
 // an instantiation through these lookups.
 #pragma once
 #include "search_kernel.cuh"
@@ -8,7 +8,7 @@ namespace bang {
 typedef void (*search_fn_t)(const SearchArgs);
 typedef void (*table_fn_t)(const SearchArgs, float*);
 
-// mode: 0 Base / 1 Inmemory / 2 Exactdistance; cs: uniform PQ chunk size 4, 3 or 0 (general); wpc: 16, 24 or 32 (wpc_variant)
+// mode: 0 Base / 1 Inmemory / 2 Exactdistance; cs: 4 (32 uniform chunks, padded to 4 dimensions) or 0 (general); wpc: 16, 24 or 32 (wpc_variant)
 search_fn_t search_kernel_u8(int mode, uint32_t cs, int wpc);
 search_fn_t search_kernel_i8(int mode, uint32_t cs, int wpc);
 search_fn_t search_kernel_f32(int mode, uint32_t cs, int wpc);
@@ -28,11 +28,7 @@ static search_fn_t inst_wpc(int mode, int wpc) {
 template <typename T>
 static search_fn_t inst_lookup(int mode, uint32_t cs, int wpc) {
   if (mode == kExact) return bang_search_kernel<T, kExact, 0, 16>;
-  switch (cs) {
-    case 4: return inst_wpc<T, 4>(mode, wpc);
-    case 3: return inst_wpc<T, 3>(mode, wpc);
-    default: return inst_wpc<T, 0>(mode, wpc);
-  }
+  return cs == 4 ? inst_wpc<T, 4>(mode, wpc) : inst_wpc<T, 0>(mode, wpc);
 }
 #endif
 }  // namespace bang

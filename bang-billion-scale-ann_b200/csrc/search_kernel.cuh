@@ -50,7 +50,8 @@ namespace bang {
 constexpr int kThreads = 32;            // threads per query = one warp (see the header comment)
 constexpr int kMaxWarpsPerCta = 32;  // PQ modes: one CTA of up to 32 query warps per SM (kernels compiled for 16 / 24 / 32, see bang_search_kernel)
 constexpr int kMaxR = 64;               // MAX_R, bang_search.cu:35
-constexpr int kListCap = kMaxR + 2;     // medoid + R neighbours (65), padded to an even count
+constexpr int kListCap = kMaxR + 4;     // medoid + R neighbours (65), padded so that every list is a multiple of 16 bytes
+constexpr uint32_t kVisitedBit = 0x80000000u;  // worklist entries carry their visited flag in the top bit of the id word (ids < 2^31, checked at load)
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
 // The visited filter has the reference's semantics — a 399887-slot bit array addressed by two hashes — but is
 // stored sparsely: 1569 blocks of 255 slots, each block = 8 bytes holding up to 7 one-byte offsets of its set
@@ -84,8 +85,10 @@ struct SearchArgs {
   uint32_t code_stride;
   uint32_t n_chunks;
   const float* pivT;        // [D][256]   pivots transposed as the reference does at load (:281-285); stage-1 kernel only
-  const float* piv;         // [256][D]   pivots in file order: the shared-memory table of the search kernel
-  uint32_t chunk4;          // 4 or 3 when there are exactly 32 chunks of that many dimensions each (selects the CS kernel), else 0
+  const float* piv;         // [256][piv_row]  the search kernel's pivot table (copied into shared memory once per CTA): file order
+                            //            [256][D], or, for the CS = 4 kernels, every chunk zero-padded to 4 dimensions ([256][32][4])
+  uint32_t piv_row;         // floats per row of `piv`: D, or 128 for the padded table
+  uint32_t chunk4;          // 1..4 when there are exactly 32 chunks of that many dimensions each (selects the CS = 4 kernel), else 0
   const float* centroid;    // [D]
   const uint32_t* chunk_off;  // [n_chunks+1]
   uint32_t D;               // dims of the index
@@ -103,6 +106,7 @@ struct SearchArgs {
   uint32_t* cand_log;       // device: expanded-node log, cand_cap ids per resident query warp (PQ modes; read back by the re-rank)
   uint32_t piv_global;      // 1: the pivot table stays in global memory (it does not fit in shared memory: D above ~215)
   uint32_t code_prefetch;   // 1: request the PQ codes of every neighbour towards L2 while the filter is consulted
+  uint32_t row_prefetch;    // 1: at the start of a hop, request the row of the closest unexpanded worklist entry towards L2 (the likely next node)
   uint32_t stop_on_empty_hop;  // 1 (Exactdistance searches): a hop without new neighbours ends the query, see the kernel; 0 for the index builder
   uint32_t* counter;        // device work counter (zeroed before launch)
   uint32_t* st_hops;        // device [Q] or null
@@ -344,13 +348,13 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct QState {
-  const float* piv_s;       // [256][D] pivots: the CTA-shared copy, or the global table when it does not fit (PQ modes)
+  uint32_t lane;            // %laneid, read once per kernel (through volatile asm: ptxas otherwise re-reads the special register all over the hot loop)
+  uint32_t piv_sa, qc_sa;   // shared-space byte addresses of the pivot table and of this warp's query residual (CS = 4 ADC path)
+  const float* piv_s;       // [256][piv_row] pivots: the CTA-shared copy, or the global table when it does not fit (PQ modes)
   const uint32_t* coff_s;   // [n_chunks+1] chunk offsets (CTA-shared, PQ modes)
   float* q_f;        // [vec_units * E] query as fp32, zero padded (PQ modes: only during the re-rank, in place of qc)
-  float* qc;         // [D] query - centroid (PQ modes, during the traversal)
-  float* w_d;        // worklist [w_cap], sorted by distance
-  uint32_t* w_id;
-  uint8_t* w_v;      // visited flags
+  float* qc;         // [piv_row] query - centroid, laid out like a pivot-table row (PQ modes, during the traversal)
+  uint2* w;          // worklist [w_cap], sorted by distance: .x = distance bits, .y = id | kVisitedBit if expanded
   uint32_t* n_id;    // [kListCap] filtered neighbours of this hop, unordered
   float* n_d;
   uint32_t* s_id;    // [kListCap] the admitted ones, sorted by (dist, id)
@@ -364,19 +368,28 @@ struct QState {
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // CTA-shared bytes
-__host__ __device__ inline size_t cta_shared_bytes(int mode, uint32_t D, uint32_t n_chunks, bool piv_global) {
+__host__ __device__ inline size_t cta_shared_bytes(int mode, uint32_t piv_row, uint32_t n_chunks, bool piv_global) {
   if (mode == kExact) return 0;
-  return (piv_global ? 0 : align_up((size_t)256 * D * 4, 16)) + align_up((size_t)(n_chunks + 1) * 4, 16);
+  return (piv_global ? 0 : align_up((size_t)256 * piv_row * 4, 16)) + align_up((size_t)(n_chunks + 1) * 4, 16);
 }
+// floats per row of the search kernel's pivot table: 32 uniform chunks of up to 4 dimensions are zero-padded to 4 each
+// (one 16-byte shared-memory load per table entry; a zero dimension adds fmaf(0, 0, acc) = acc, so the sums keep their bits)
+__host__ __device__ inline uint32_t pivot_row_floats(uint32_t D, uint32_t chunk4) { return chunk4 ? 128u : D; }
 // Private bytes per warp (= per resident query): [query block][worklist | neighbour lists].  PQ modes keep
 // query - centroid in the query block during the traversal and the fp32 query during the re-rank, whose exact
 // distances and candidate ids reuse the (then dead) worklist + list block; the expanded-node log itself lives in
 // global memory — 3152 B per query at D = 128, L = 176, so that 32 queries fit next to the 128 KB pivot table.
 // Exactdistance keeps the fp32 query throughout.
 template <typename T>
-__host__ __device__ inline size_t warp_private_bytes(int mode, uint32_t D, uint32_t vec_units, uint32_t L, uint32_t cand_cap) {
-  const size_t qf = align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);  // >= D * 4
-  size_t walk = align_up(L, 16) * 9 + (size_t)kListCap * 4 * 4;  // worklist (dist + id + visited) + n_id/n_d/s_id/s_d
+__host__ __device__ inline size_t query_block_bytes(int mode, uint32_t piv_row, uint32_t vec_units) {
+  size_t qf = align_up((size_t)vec_units * Elem<T>::kPerUnit * 4, 16);  // >= D * 4
+  if (mode != kExact && qf < (size_t)piv_row * 4) qf = (size_t)piv_row * 4;  // (padded residual)
+  return qf;
+}
+template <typename T>
+__host__ __device__ inline size_t warp_private_bytes(int mode, uint32_t piv_row, uint32_t vec_units, uint32_t L, uint32_t cand_cap) {
+  const size_t qf = query_block_bytes<T>(mode, piv_row, vec_units);
+  size_t walk = align_up(L, 16) * 8 + (size_t)kListCap * 4 * 4;  // worklist (8 bytes per entry) + n_id/n_d/s_id/s_d
   if (mode != kExact && walk < (size_t)cand_cap * 8) walk = (size_t)cand_cap * 8;  // (never the case for cand_cap <= L + 121)
   return align_up(qf + walk, 16);
 }
@@ -386,18 +399,19 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
   size_t o = 0;
   const bool pg = a.piv_global != 0;
   s.piv_s = pg ? a.piv : (const float*)(base + o);
-  s.coff_s = (const uint32_t*)(base + (pg ? 0 : align_up((size_t)256 * a.D * 4, 16)));
-  o += cta_shared_bytes(mode, a.D, a.n_chunks, pg);
-  o += (size_t)warp * warp_private_bytes<T>(mode, a.D, a.vec_units, a.L, a.cand_cap);
+  s.coff_s = (const uint32_t*)(base + (pg ? 0 : align_up((size_t)256 * a.piv_row * 4, 16)));
+  o += cta_shared_bytes(mode, a.piv_row, a.n_chunks, pg);
+  o += (size_t)warp * warp_private_bytes<T>(mode, a.piv_row, a.vec_units, a.L, a.cand_cap);
   s.qc = (float*)(base + o);
   s.q_f = (float*)(base + o);
-  o += align_up((size_t)a.vec_units * Elem<T>::kPerUnit * 4, 16);
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(base);
+  s.piv_sa = sbase;
+  s.qc_sa = sbase + (uint32_t)o;
+  o += query_block_bytes<T>(mode, a.piv_row, a.vec_units);
   s.cd = (float*)(base + o);
   s.cid = (uint32_t*)(base + o) + a.cand_cap;
   const size_t wcap = align_up(a.L, 16);
-  s.w_d = (float*)(base + o); o += wcap * 4;
-  s.w_id = (uint32_t*)(base + o); o += wcap * 4;
-  s.w_v = (uint8_t*)(base + o); o += wcap;
+  s.w = (uint2*)(base + o); o += wcap * 8;
   s.n_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
   s.n_d = (float*)(base + o); o += (size_t)kListCap * 4;
   s.s_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
@@ -435,48 +449,82 @@ __device__ __forceinline__ void build_pq_table(const SearchArgs& a, const float*
 
 // One table entry on demand: the identical operation sequence as build_pq_table for (chunk c, centre `code`),
 // reading the pivot row from the CTA-shared table — hence bit-identical to the reference's tbl[c][code].
-template <int CS>  // CS = uniform chunk size known at compile time (4: 16-byte loads; 3), or 0 = read the chunk offsets
+// General layout (any chunk offsets, any number of chunks); the 32-uniform-chunk kernels use adc4 below.
 __device__ __forceinline__ float adc_entry(const QState& s, uint32_t D, uint32_t c, uint32_t code) {
   float acc = 0.0f;
-  if (CS == 4) {
-    // 32-bit shared-space addresses, one 16-byte load each for the pivot row slice and the query residual
-    const uint32_t pa = (uint32_t)__cvta_generic_to_shared(s.piv_s) + (code * D + 4u * c) * 4u;
-    const uint32_t qa = (uint32_t)__cvta_generic_to_shared(s.qc) + 16u * c;
-    float4 pv, qv;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w) : "r"(pa));
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(qv.x), "=f"(qv.y), "=f"(qv.z), "=f"(qv.w) : "r"(qa));
-    float d;
-    d = __fsub_rn(pv.x, qv.x); acc = __fmaf_rn(d, d, acc);
-    d = __fsub_rn(pv.y, qv.y); acc = __fmaf_rn(d, d, acc);
-    d = __fsub_rn(pv.z, qv.z); acc = __fmaf_rn(d, d, acc);
-    d = __fsub_rn(pv.w, qv.w); acc = __fmaf_rn(d, d, acc);
-  } else if (CS > 0) {
-    const float* p = s.piv_s + (size_t)code * D + CS * c;
-    const float* qv = s.qc + CS * c;
-#pragma unroll
-    for (int j = 0; j < CS; ++j) { const float d = __fsub_rn(p[j], qv[j]); acc = __fmaf_rn(d, d, acc); }
-  } else {
-    const float* p = s.piv_s + (size_t)code * D;
-    const uint32_t j0 = s.coff_s[c], j1 = s.coff_s[c + 1];
-    for (uint32_t j = j0; j < j1; ++j) { const float d = __fsub_rn(p[j], s.qc[j]); acc = __fmaf_rn(d, d, acc); }
-  }
+  const float* p = s.piv_s + (size_t)code * D;
+  const uint32_t j0 = s.coff_s[c], j1 = s.coff_s[c + 1];
+  for (uint32_t j = j0; j < j1; ++j) { const float d = __fsub_rn(p[j], s.qc[j]); acc = __fmaf_rn(d, d, acc); }
   return acc;
 }
 
 // partial ADC sum of one 32-chunk group for lane t: chunks base+t, base+t+8, base+t+16, base+t+24 (ascending).
-// FULL: the group is known to be complete (n_chunks is a multiple of 32), no bounds checks.
-template <int CS, bool FULL>
 __device__ __forceinline__ float adc_group(const QState& s, const SearchArgs& a, uint32_t word, uint32_t base, uint32_t t, float sum) {
   float e[4];
 #pragma unroll
   for (int b = 0; b < 4; ++b) {  // four independent chains, then the ordered sum
     const uint32_t c = base + t + 8 * b;
-    e[b] = (FULL || c < a.n_chunks) ? adc_entry<CS>(s, a.D, c, (word >> (8 * b)) & 0xff) : 0.0f;
+    e[b] = c < a.n_chunks ? adc_entry(s, a.D, c, (word >> (8 * b)) & 0xff) : 0.0f;
   }
 #pragma unroll
   for (int b = 0; b < 4; ++b)
-    if (FULL || base + t + 8 * b < a.n_chunks) sum = __fadd_rn(sum, e[b]);
+    if (base + t + 8 * b < a.n_chunks) sum = __fadd_rn(sum, e[b]);
   return sum;
+}
+
+// ---- the CS = 4 ADC path: 32 chunks, every chunk padded to 4 dimensions -----------------------------------
+// The shared pivot table is [256][32][4] floats (512 bytes per centre), the query residual one such row.  Lane t of an
+// 8-lane group owns chunks t, t+8, t+16, t+24: its four residual slices (16 floats) are loaded once per hop, a table
+// entry is one 16-byte shared-memory load at  table + code * 512 + chunk * 16  and the fmaf chain of build_pq_table.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds_f4_off(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+  return v;
+}
+// pa + 512 * (byte B of word): one byte permute + one multiply-add
+template <int B>
+__device__ __forceinline__ uint32_t entry_addr(uint32_t pa, uint32_t word) {
+  uint32_t code, addr;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(code) : "r"(word), "n"(0x4440 + B));
+  asm("mad.lo.u32 %0, %1, 512, %2;" : "=r"(addr) : "r"(code), "r"(pa));
+  return addr;
+}
+__device__ __forceinline__ float adc4_chain(const float4 p, const float4 q) {
+#ifndef BANG_ADC_SCALAR_SUB
+  // the four subtractions as two packed fp32x2 operations (round-to-nearest per element: the same bits)
+  unsigned long long p01, p23, q01, q23, d01, d23;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(p01) : "f"(p.x), "f"(p.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(p23) : "f"(p.z), "f"(p.w));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(q01) : "f"(q.x), "f"(q.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(q23) : "f"(q.z), "f"(q.w));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(p01), "l"(q01));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(p23), "l"(q23));
+  float d0, d1, d2, d3;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d01));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(d2), "=f"(d3) : "l"(d23));
+#else
+  const float d0 = __fsub_rn(p.x, q.x), d1 = __fsub_rn(p.y, q.y), d2 = __fsub_rn(p.z, q.z), d3 = __fsub_rn(p.w, q.w);
+#endif
+  float acc = __fmaf_rn(d0, d0, 0.0f);
+  acc = __fmaf_rn(d1, d1, acc);
+  acc = __fmaf_rn(d2, d2, acc);
+  return __fmaf_rn(d3, d3, acc);
+}
+// lane t's share of one candidate's PQ distance: entries of chunks t, t+8, t+16, t+24 (the four bytes of `word`), summed
+// in ascending chunk order from 0.0f (0.0f + e = e exactly: every entry is >= +0)
+__device__ __forceinline__ float adc4_word(uint32_t pa /* table + 16 t */, uint32_t word, const float4& q0, const float4& q1, const float4& q2,
+                                           const float4& q3) {
+  // the four table loads are issued back to back (volatile asm keeps them in this order), then the four chains
+  const float4 p0 = lds_f4_off<0>(entry_addr<0>(pa, word)), p1 = lds_f4_off<128>(entry_addr<1>(pa, word));
+  const float4 p2 = lds_f4_off<256>(entry_addr<2>(pa, word)), p3 = lds_f4_off<384>(entry_addr<3>(pa, word));
+  const float e0 = adc4_chain(p0, q0), e1 = adc4_chain(p1, q1), e2 = adc4_chain(p2, q2), e3 = adc4_chain(p3, q3);
+  return __fadd_rn(__fadd_rn(__fadd_rn(e0, e1), e2), e3);
 }
 
 template <typename T>
@@ -487,16 +535,23 @@ __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, floa
 }
 // query - centroid (populate_pqDist_par's `query[j] - centroid[j]`, bang_search.cu:1118-1129); a MIPS query is
 // padded with one zero dimension (bang_search.cu:1099-1113)
-template <typename T>
+template <typename T, int CS>
 __device__ __forceinline__ void load_query_residual(const SearchArgs& a, uint32_t q, float* qc) {
   const T* src = reinterpret_cast<const T*>(a.queries) + (size_t)q * a.q_dim;
+  if (CS == 4) {  // laid out like a row of the padded pivot table: chunk c at floats 4c .. 4c+3, zero beyond the chunk's dimensions
+    for (uint32_t i = threadIdx.x & 31; i < 128u; i += 32) {
+      const uint32_t e = i & 3u, j = (i >> 2) * a.chunk4 + e;
+      qc[i] = e < a.chunk4 ? __fsub_rn(j < a.q_dim ? (float)src[j] : 0.0f, __ldg(a.centroid + j)) : 0.0f;
+    }
+    return;
+  }
   for (uint32_t j = threadIdx.x & 31; j < a.D; j += 32) qc[j] = __fsub_rn(j < a.q_dim ? (float)src[j] : 0.0f, __ldg(a.centroid + j));
 }
 
 // adjacency prefetch: lane l requests neighbour slots 2l and 2l+1 of `node`'s HBM row (one 256-byte request)
-__device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream) {
+__device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream, uint32_t lane) {
   uint2 r;
-  const uint8_t* p = row_ptr(a, node) + 8 * (threadIdx.x & 31);
+  const uint8_t* p = row_ptr(a, node) + 8 * lane;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
                : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_stream));
   return r;
@@ -572,7 +627,7 @@ __device__ __forceinline__ VisPos vis_pos(uint32_t id) {
 template <typename T, int MODE, int CS>
 __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* vis, uint32_t* vbm, uint2 nb2, bool first,
                                            Prof& pf) {
-  const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+  const uint32_t lane = s.lane, lt = (1u << lane) - 1u;
   const uint32_t id0 = nb2.x, id1 = nb2.y;
   const bool v0 = id0 != kNoNbr, v1 = id1 != kNoNbr;
 #ifdef BANG_PHASE_TIMERS
@@ -661,27 +716,29 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       if (t == 0 && kb < n) s.n_d[kb] = db;
     }
   } else if (CS > 0) {
-    // uniform chunks and exactly 32 of them (C2 / C4 / C5: D = 128 or 96, 32 bytes per vector): lane t's four chunks
-    // t, t+8, t+16, t+24 are one 32-bit word.  The code words of up to 16 candidates are requested at once; the
-    // table entries are evaluated four candidates (one per 8-lane group) at a time.
+    // 32 uniform chunks (C2 / C4 / C5: D = 128 or 96, 32 bytes per vector): lane t's chunks t, t+8, t+16, t+24 are one 32-bit
+    // code word.  The code words of up to 16 candidates are requested at once; the table entries are evaluated four
+    // candidates (one per 8-lane group) at a time.
+    const uint32_t pa = s.piv_sa + 16u * t, qa = s.qc_sa + 16u * t;
+    const float4 q0 = lds_f4_off<0>(qa), q1 = lds_f4_off<128>(qa), q2 = lds_f4_off<256>(qa), q3 = lds_f4_off<384>(qa);
+    const uint8_t* cbase = a.codes + 4 * t;  // (32 chunks: 32-byte code rows)
     for (uint32_t k0 = 0; k0 < n; k0 += 16) {
-      uint32_t w[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const uint32_t k = k0 + p * 4 + g;
-        w[p] = 0;
-        if (k < n) w[p] = ld_nc_u32(a.codes + (size_t)s.n_id[k] * a.code_stride + 4 * t, s.pol_stream);
-      }
+      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      const uint32_t kg = k0 + g;
+      if (kg < n) w0 = ld_nc_u32(cbase + (size_t)s.n_id[kg] * 32u, s.pol_stream);
+      if (kg + 4 < n) w1 = ld_nc_u32(cbase + (size_t)s.n_id[kg + 4] * 32u, s.pol_stream);
+      if (kg + 8 < n) w2 = ld_nc_u32(cbase + (size_t)s.n_id[kg + 8] * 32u, s.pol_stream);
+      if (kg + 12 < n) w3 = ld_nc_u32(cbase + (size_t)s.n_id[kg + 12] * 32u, s.pol_stream);
 #ifdef BANG_PHASE_TIMERS
-      if (__any_sync(kFull, (w[0] ^ w[1] ^ w[2] ^ w[3]) == 0x12345678u)) printf("");
+      if (__any_sync(kFull, (w0 ^ w1 ^ w2 ^ w3) == 0x12345678u)) printf("");
       pf.tick(PT_CODEWAIT);
 #endif
+      const uint32_t kend = min(n, k0 + 16);
 #pragma unroll 1
-      for (uint32_t p = 0; p < 4 && k0 + p * 4 < n; ++p) {  // (not unrolled: the kernel's hot loop has to stay inside the instruction cache)
-        const uint32_t k = k0 + p * 4 + g;
-        const uint32_t wp = p == 0 ? w[0] : (p == 1 ? w[1] : (p == 2 ? w[2] : w[3]));
-        const float sum = tree8(adc_group<CS, true>(s, a, wp, 0, t, 0.0f));
-        if (t == 0 && k < n) s.n_d[k] = sum;
+      for (uint32_t kb = k0; kb < kend; kb += 4) {  // (not unrolled: the kernel's hot loop has to stay inside the instruction cache)
+        const float sum = tree8(adc4_word(pa, w0, q0, q1, q2, q3));
+        if (t == 0 && kb + g < n) s.n_d[kb + g] = sum;
+        w0 = w1; w1 = w2; w2 = w3;
       }
     }
   } else {
@@ -694,8 +751,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       for (uint32_t gg = 0; gg < groups; gg += 2) {
         const uint32_t wa = ld_nc_u32(row + gg * 32, s.pol_stream);
         const uint32_t wb = (gg + 1 < groups) ? ld_nc_u32(row + (gg + 1) * 32, s.pol_stream) : 0u;
-        sum = adc_group<CS, false>(s, a, wa, gg * 32, t, sum);
-        sum = adc_group<CS, false>(s, a, wb, (gg + 1) * 32, t, sum);
+        sum = adc_group(s, a, wa, gg * 32, t, sum);
+        sum = adc_group(s, a, wb, (gg + 1) * 32, t, sum);
       }
       sum = tree8(sum);
       if (t == 0 && k < n) s.n_d[k] = sum;
@@ -709,7 +766,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
 
 // lane 0's statistics (kept in the lists' spare slots, see expand) go to global before the re-rank reuses the block
 __device__ __forceinline__ void write_stats(const SearchArgs& a, const QState& s, uint32_t q) {
-  if ((threadIdx.x & 31) == 0) {
+  if (s.lane == 0) {
     if (a.st_sumdeg) a.st_sumdeg[q] = s.n_id[kListCap - 1];
     if (a.st_npass) a.st_npass[q] = s.s_id[kListCap - 1];
   }
@@ -721,15 +778,24 @@ __device__ __forceinline__ void write_stats(const SearchArgs& a, const QState& s
 // patterns order like the floats and redux.sync (min/add over the warp) does the reductions.
 struct Best { float d; uint32_t id; uint32_t below; float med_d; bool med_in; };
 __device__ __forceinline__ Best scan_neighbours(const QState& s, uint32_t n, uint32_t medoid, bool skip_medoid, float maxd) {
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = s.lane;
   uint32_t bd = 0x7F7FFFFFu /* FLT_MAX */, bid = kNone, below = 0, md = 0;
   bool mi = false;
-  for (uint32_t i = lane; i < n; i += 32) {
-    const float d = s.n_d[i];
-    const uint32_t id = s.n_id[i], db = __float_as_uint(d);
-    below += d < maxd ? 1u : 0u;
-    if (id == medoid) { mi = true; md = db; if (skip_medoid) continue; }
-    if (db < bd || (db == bd && id < bid)) { bd = db; bid = id; }
+  if (skip_medoid) {  // the first hop: the list starts with the medoid itself, which is not a candidate for expansion
+    for (uint32_t i = lane; i < n; i += 32) {
+      const float d = s.n_d[i];
+      const uint32_t id = s.n_id[i], db = __float_as_uint(d);
+      below += d < maxd ? 1u : 0u;
+      if (id == medoid) { mi = true; md = db; continue; }
+      if (db < bd || (db == bd && id < bid)) { bd = db; bid = id; }
+    }
+  } else {            // every later hop (med_in / med_d are only read on the first)
+    for (uint32_t i = lane; i < n; i += 32) {
+      const float d = s.n_d[i];
+      const uint32_t id = s.n_id[i], db = __float_as_uint(d);
+      below += d < maxd ? 1u : 0u;
+      if (db < bd || (db == bd && id < bid)) { bd = db; bid = id; }
+    }
   }
   Best b;
   const uint32_t dmin = __reduce_min_sync(kFull, bd);
@@ -744,10 +810,10 @@ __device__ __forceinline__ Best scan_neighbours(const QState& s, uint32_t n, uin
 
 // first unvisited worklist entry at or after `start`
 __device__ __forceinline__ uint32_t scan_unvisited(const QState& s, uint32_t start, uint32_t ws) {
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = s.lane;
   for (uint32_t b0 = start; b0 < ws; b0 += 32) {
     const uint32_t j = b0 + lane;
-    const uint32_t m = __ballot_sync(kFull, j < ws && s.w_v[j] == 0);
+    const uint32_t m = __ballot_sync(kFull, j < ws && (s.w[j].y & kVisitedBit) == 0);
     if (m) return b0 + (uint32_t)__ffs(m) - 1u;
   }
   return kNone;
@@ -762,7 +828,7 @@ __device__ __forceinline__ uint32_t admit_count(uint32_t below, uint32_t n, uint
 // Common case (worklist full): the admitted set is exactly the entries closer than the current tail, a
 // handful per hop — compacted with ballots and ranked through shuffles.  Otherwise: rank among all n.
 __device__ __forceinline__ void select_admitted(const QState& s, uint32_t n, uint32_t nb, uint32_t below, float maxd) {
-  const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+  const uint32_t lane = s.lane, lt = (1u << lane) - 1u;
   if (nb == below && nb <= 32) {
     uint32_t base = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
@@ -804,23 +870,67 @@ __device__ __forceinline__ void select_admitted(const QState& s, uint32_t n, uin
 // only from the first insertion point on, so nothing is overwritten before it is read.
 // Returns the new size; *pos0 = position of the closest new entry.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float w_dist(const QState& s, uint32_t j) { return __uint_as_float(s.w[j].x); }
 __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QState& s, uint32_t n, uint32_t nb, uint32_t below,
                                                    float maxd, uint32_t ws, bool first, uint32_t flag_id, uint32_t* pos0) {
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = s.lane;
   select_admitted(s, n, nb, first ? kNone : below, maxd);
   if (first) {  // iter == 1 branch (:1636-1646): the worklist is the head of the sorted list
     for (uint32_t i = lane; i < nb; i += 32) {
       const uint32_t id = s.s_id[i];
-      s.w_d[i] = s.s_d[i];
-      s.w_id[i] = id;
-      s.w_v[i] = (id == a.medoid || id == flag_id) ? 1 : 0;
+      s.w[i] = make_uint2(__float_as_uint(s.s_d[i]), id | ((id == a.medoid || id == flag_id) ? kVisitedBit : 0u));
     }
     __syncwarp();
     *pos0 = 0;
     return nb;
   }
   const uint32_t newsize = min(ws + nb, a.L);
-  // new entries: position = index + lower_bound(W, d)  (new before old on ties); nb <= 65 -> at most 3 per lane
+  if (nb <= 4) {
+    // The common case once the worklist is full: a handful of new entries.  Their distances sit in registers of every
+    // lane (+inf beyond nb); one pass over the old entries from the tail, 32 at a time, moves each by the number of new
+    // entries at or below it (new before old on ties) and counts, per new entry, the old entries that stay in front of
+    // it (= its lower bound) with one ballot each — no dependent shared-memory searches.  The pass stops at the first
+    // chunk that lies entirely below the closest new entry.
+    const float inf = __uint_as_float(0x7F800000u);
+    const float4 sd = *reinterpret_cast<const float4*>(s.s_d);  // (the lists are 16-byte aligned)
+    const float nd0 = sd.x, nd1 = nb > 1 ? sd.y : inf, nd2 = nb > 2 ? sd.z : inf, nd3 = nb > 3 ? sd.w : inf;
+    uint32_t lb0 = 0, lb1 = 0, lb2 = 0, lb3 = 0;
+    for (int c = (int)((ws - 1) >> 5); c >= 0; --c) {
+      const uint32_t j = (uint32_t)c * 32 + lane;
+      const bool live = j < ws;
+      uint2 e = make_uint2(0x7F800000u, 0u);
+      if (live) e = s.w[j];
+      const float d = __uint_as_float(e.x);
+      const bool l0 = d < nd0, l1 = d < nd1, l2 = d < nd2, l3 = d < nd3;
+      const uint32_t b0 = __ballot_sync(kFull, l0);
+      lb0 += __popc(b0);
+      lb1 += __popc(__ballot_sync(kFull, l1));
+      lb2 += __popc(__ballot_sync(kFull, l2));
+      lb3 += __popc(__ballot_sync(kFull, l3));
+      const uint32_t pos = j + (l0 ? 0u : 1u) + (l1 ? 0u : 1u) + (l2 ? 0u : 1u) + (l3 ? 0u : 1u);  // (dead lanes: >= ws + 4, never stored... see below)
+      __syncwarp();
+      if (live && pos < newsize) s.w[pos] = e;
+      __syncwarp();
+      if (b0 == kFull) {  // everything from here down is closer than every new entry and stays where it is
+        const uint32_t rest = (uint32_t)c * 32;
+        lb0 += rest; lb1 += rest; lb2 += rest; lb3 += rest;
+        break;
+      }
+    }
+    if (lane < nb) {
+      const uint32_t lb = lane == 0 ? lb0 : (lane == 1 ? lb1 : (lane == 2 ? lb2 : lb3));
+      const uint32_t np = lane + lb;
+      if (np < newsize) {
+        const uint32_t id = s.s_id[lane];
+        s.w[np] = make_uint2(__float_as_uint(s.s_d[lane]), id | (id == flag_id ? kVisitedBit : 0u));
+      }
+    }
+    __syncwarp();
+    *pos0 = lb0;
+    return newsize;
+  }
+  // general case (the worklist is still filling up): position = index + lower_bound(W, d)  (new before old on ties);
+  // nb <= 65 -> at most 3 per lane
   uint32_t npos[3];
 #pragma unroll
   for (int e = 0; e < 3; ++e) {
@@ -831,7 +941,7 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
       uint32_t lo = 0, hi = ws;
       while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (d <= s.w_d[mid]) hi = mid; else lo = mid + 1;
+        if (d <= w_dist(s, mid)) hi = mid; else lo = mid + 1;
       }
       npos[e] = lo + i;
     }
@@ -841,11 +951,11 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
   for (int c = (int)((ws - 1) >> 5); c >= (int)(p0 >> 5); --c) {  // old entries at or after the insertion point, tail first
     const uint32_t j = (uint32_t)c * 32 + lane;
     const bool live = j < ws && j >= p0;
-    float d = 0.0f;
-    uint32_t id = 0, pos = kNone;
-    uint8_t v = 0;
+    uint2 e = make_uint2(0u, 0u);
+    uint32_t pos = kNone;
     if (live) {
-      d = s.w_d[j]; id = s.w_id[j]; v = s.w_v[j];
+      e = s.w[j];
+      const float d = __uint_as_float(e.x);
       uint32_t lo = 0, hi = nb;
       while (lo < hi) {  // upper_bound over the admitted new entries
         const uint32_t mid = (lo + hi) >> 1;
@@ -854,7 +964,7 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
       pos = j + lo;
     }
     __syncwarp();
-    if (pos < newsize) { s.w_d[pos] = d; s.w_id[pos] = id; s.w_v[pos] = v; }
+    if (pos < newsize) s.w[pos] = e;
     __syncwarp();
   }
 #pragma unroll
@@ -862,9 +972,7 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
     const uint32_t i = lane + 32 * e;
     if (npos[e] < newsize) {
       const uint32_t id = s.s_id[i];
-      s.w_d[npos[e]] = s.s_d[i];
-      s.w_id[npos[e]] = id;
-      s.w_v[npos[e]] = (id == flag_id) ? 1 : 0;
+      s.w[npos[e]] = make_uint2(__float_as_uint(s.s_d[i]), id | (id == flag_id ? kVisitedBit : 0u));
     }
   }
   __syncwarp();
@@ -879,7 +987,7 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
-  const uint32_t lane = threadIdx.x & 31, t = lane & 7, g = lane >> 3;
+  const uint32_t lane = s.lane, t = lane & 7, g = lane >> 3;
   float* cd = s.cd;       // the worklist block is dead by now: exact distances + a copy of the log go there,
   uint32_t* cid = s.cid;  // the fp32 query where query - centroid was (see warp_private_bytes)
   __syncwarp();
@@ -929,7 +1037,9 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
 template <typename T, int MODE, int CS, int WPC>
 __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const uint32_t warps = blockDim.x >> 5;
+  uint32_t lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
   const uint32_t warp = __shfl_sync(kFull, threadIdx.x >> 5, 0);  // (through a shuffle: the compiler then knows it is warp-uniform)
   if (MODE != kExact) {
     // the pivot table (unless it stays in global memory) and the chunk offsets, once per CTA, shared by all its query warps
@@ -937,15 +1047,16 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     if (!a.piv_global) {
       float4* dst = reinterpret_cast<float4*>(smem_raw);
       const float4* src = reinterpret_cast<const float4*>(a.piv);
-      const uint32_t n4 = 256u * a.D / 4u;  // D*256 floats; 256*D*4 bytes is a multiple of 16
+      const uint32_t n4 = 256u * a.piv_row / 4u;  // piv_row*256 floats; 256*piv_row*4 bytes is a multiple of 16
       for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
-      p += align_up((size_t)256 * a.D * 4, 16);
+      p += align_up((size_t)256 * a.piv_row * 4, 16);
     }
     uint32_t* coff = reinterpret_cast<uint32_t*>(p);
     for (uint32_t i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) coff[i] = a.chunk_off[i];
     __syncthreads();  // the only CTA barrier; from here on the warps never meet again
   }
   QState s;
+  s.lane = lane;
   carve<T>(s, smem_raw, MODE, a, warp);
   const uint64_t pol_stream = l2_policy_evict_first();
   s.pol_stream = pol_stream;
@@ -964,10 +1075,10 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     Prof pf;
     pf.start();
     // ---- per-query setup: query -> smem, bloom filter cleared ----
-    uint2 my_nb = fetch_adj(a, a.medoid, pol_stream);  // the first hop's adjacency row travels during the setup
+    uint2 my_nb = fetch_adj(a, a.medoid, pol_stream, lane);  // the first hop's adjacency row travels during the setup
     __syncwarp();
     if (MODE == kExact) load_query<T>(a, q, s.q_f);
-    else load_query_residual<T>(a, q, s.qc);
+    else load_query_residual<T, CS>(a, q, s.qc);
     {  // empty filter: every offset byte 0xFF, count 0 (two 8-byte blocks per store; the padding blocks are never read)
       uint4* b4 = reinterpret_cast<uint4*>(vis);
       for (uint32_t i = lane; i < (kVisBlocks + 1) / 2; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
@@ -997,7 +1108,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       uint32_t pend_n = n, pend_nb = min(n, a.L), pend_below = 0, scan_from = 0;
       float pend_maxd = 0.0f;
       while (have || pend_n > 0) {
-        if (have) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
+        if (have) my_nb = fetch_adj(a, parent, pol_stream, lane);  // in flight during the merge
         pf.tick(PT_DECIDE);
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
           ws = merge_worklist(a, s, pend_n, pend_nb, pend_below, pend_maxd, ws, iter == 1, mark, &pos0);
@@ -1013,15 +1124,15 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         if (have) n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, pf);
         ++iter;
         // compute_parent2 (:1403-1458)
-        const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
+        const float maxd = ws > 0 ? w_dist(s, ws - 1) : 0.0f;
         b = scan_neighbours(s, n, a.medoid, true, maxd);
         pf.tick(PT_SCAN);
         const bool hasx = b.id != kNone;
         have = false;
         if (fu != kNone) {
           have = true;
-          if (hasx && b.d < s.w_d[fu]) { parent = b.id; mark = b.id; }
-          else { parent = s.w_id[fu]; if (lane == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
+          if (hasx && b.d < w_dist(s, fu)) { parent = b.id; mark = b.id; }
+          else { parent = s.w[fu].y; if (lane == 0) s.w[fu].y = parent | kVisitedBit; scan_from = fu + 1; }  // (fu is unvisited: no flag in the id word)
         } else if (ws > 0 && hasx && b.d < maxd) {
           have = true; parent = b.id; mark = b.id;
         }
@@ -1043,12 +1154,15 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
+        // the closest unexpanded worklist entry is the next node to expand unless this hop finds a closer one: its
+        // adjacency row starts travelling towards L2 now, a whole hop before it is needed
+        if (a.row_prefetch && fu != kNone) prefetch_l2(row_ptr(a, s.w[fu].y) + 8 * lane);
         const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, pf);
         // Exactdistance: a hop whose neighbours are all filtered out ends the query — what the reference's fused
         // kernel does when built for sm_100a (it scans the worklist up to a size it only sets when there are new
         // neighbours, BANG_Exactdistance/parANN.cu:1593,1600,1671; pinned by tests/golden/ref_forks_golden.npz).
         if (MODE == kExact && a.stop_on_empty_hop && !first && n == 0) break;
-        const float maxd = ws > 0 ? s.w_d[ws - 1] : 0.0f;
+        const float maxd = ws > 0 ? w_dist(s, ws - 1) : 0.0f;
         const Best b = scan_neighbours(s, n, a.medoid, first, maxd);
         pf.tick(PT_SCAN);
         pf.count(PT_HOPS);
@@ -1060,21 +1174,21 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
           if (b.id != kNone && rank_x < nb) { have = true; from_new = true; parent = b.id; }
         } else {
           nb = n ? admit_count(b.below, n, ws, a.L) : 0u;
-          if (nb > 0 && (fu == kNone || b.d <= s.w_d[fu])) { have = true; from_new = true; parent = b.id; }
-          else if (fu != kNone) { have = true; parent = s.w_id[fu]; }
+          if (nb > 0 && (fu == kNone || b.d <= w_dist(s, fu))) { have = true; from_new = true; parent = b.id; }
+          else if (fu != kNone) { have = true; parent = s.w[fu].y; }  // (unvisited: no flag in the id word)
         }
         if (!have) {  // nothing unvisited and nothing admitted: the merge would be a no-op — except on a first hop whose
           if (first && nb > 0) {  // sorted list starts with the medoid and offers nothing else: the worklist is [medoid, visited]
-            if (lane == 0) { s.w_id[0] = a.medoid; s.w_d[0] = b.med_d; s.w_v[0] = 1; }
+            if (lane == 0) s.w[0] = make_uint2(__float_as_uint(b.med_d), a.medoid | kVisitedBit);
             ws = 1;
           }
           break;
         }
         uint32_t scan_from = fu == kNone ? ws : fu;
-        if (!from_new) { if (lane == 0) s.w_v[fu] = 1; scan_from = fu + 1; }
+        if (!from_new) { if (lane == 0) s.w[fu].y = parent | kVisitedBit; scan_from = fu + 1; }
         log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
         const bool capped = iter == a.max_iter - 1;
-        if (!capped) my_nb = fetch_adj(a, parent, pol_stream);  // in flight during the merge
+        if (!capped) my_nb = fetch_adj(a, parent, pol_stream, lane);  // in flight during the merge
         pf.tick(PT_DECIDE);
         if (nb > 0) {
           ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, first, from_new ? parent : kNone, &pos0);
@@ -1093,8 +1207,8 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         // top-k = head of the worklist (Exact parANN.cu:1273-1276)
         __syncwarp();
         for (uint32_t r = lane; r < a.k; r += 32) {
-          a.out_ids[(size_t)q * a.k + r] = r < ws ? (uint64_t)s.w_id[r] : 0xFFFFFFFFull;
-          a.out_dists[(size_t)q * a.k + r] = r < ws ? s.w_d[r] : 3.402823466e+38f;
+          a.out_ids[(size_t)q * a.k + r] = r < ws ? (uint64_t)(s.w[r].y & ~kVisitedBit) : 0xFFFFFFFFull;
+          a.out_dists[(size_t)q * a.k + r] = r < ws ? w_dist(s, r) : 3.402823466e+38f;
         }
       } else {
         rerank_and_write<T>(a, s, q, ncand);
@@ -1134,9 +1248,9 @@ struct LaunchGeom { int warps_per_cta; int ctas_per_sm; size_t smem; };
 // the kernel variant (WPC) that runs `warps` query warps per CTA
 inline int wpc_variant(int mode, int warps) { return (mode == kExact || warps <= 16) ? 16 : (warps <= 24 ? 24 : 32); }
 template <typename T>
-inline LaunchGeom launch_geometry(int mode, uint32_t D, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap,
+inline LaunchGeom launch_geometry(int mode, uint32_t piv_row, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap,
                                   size_t smem_optin_per_block, size_t smem_per_sm, int max_warps_per_sm, bool piv_global = false) {
-  const size_t shared = cta_shared_bytes(mode, D, n_chunks, piv_global), per = warp_private_bytes<T>(mode, D, vec_units, L, cand_cap);
+  const size_t shared = cta_shared_bytes(mode, piv_row, n_chunks, piv_global), per = warp_private_bytes<T>(mode, piv_row, vec_units, L, cand_cap);
   LaunchGeom g{0, 0, 0};
   if (shared + per > smem_optin_per_block) return g;
   int w = (int)((smem_optin_per_block - shared) / per);
