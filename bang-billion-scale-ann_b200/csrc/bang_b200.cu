@@ -157,7 +157,6 @@ struct bang_b200_ctx {
   unsigned long long* d_bad = nullptr;  // row validation counters: degree > R, id >= N, duplicate id (see validate_row)
   bool piv_global = false;              // the pivot table does not fit in shared memory: read it from global/L2
   bool code_prefetch = true;            // speculative L2 prefetch of every neighbour's PQ code row (BANG_B200_CODE_PREFETCH)
-  bool row_prefetch = false;            // L2 prefetch of the likely next node's row at the start of each hop (BANG_B200_ROW_PREFETCH)
   // params
   int k = 0, L = 0, distfn = BANG_DIST_L2, dists_layout = BANG_DISTS_RANK_MAJOR;
   // per-alloc scratch
@@ -204,12 +203,12 @@ static table_fn_t pick_table_kernel(int dtype) {
   }
 }
 static LaunchGeom geometry_for(const bang_b200_ctx* c, uint32_t L, uint32_t cand_cap, size_t optin, size_t per_sm, int max_warps,
-                               bool piv_global) {
+                               bool piv_global, bool keep_l1) {
   const uint32_t piv_row = pivot_row_floats(c->D, piv_global ? 0 : c->chunk4);
   switch (c->dtype) {
-    case BANG_DT_FLOAT: return launch_geometry<float>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
-    case BANG_DT_INT8: return launch_geometry<int8_t>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
-    default: return launch_geometry<uint8_t>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global);
+    case BANG_DT_FLOAT: return launch_geometry<float>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global, keep_l1);
+    case BANG_DT_INT8: return launch_geometry<int8_t>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global, keep_l1);
+    default: return launch_geometry<uint8_t>(c->mode, piv_row, c->n_chunks, c->vec_units, L, cand_cap, optin, per_sm, max_warps, piv_global, keep_l1);
   }
 }
 static uint32_t max_iter_for(int mode, int L) {
@@ -673,16 +672,16 @@ static int alloc_impl(bang_b200_ctx* c, int Q) {
   // registers each) — 16 (128 registers) and 32 (64 registers) are within 2-7 % on C2 / DEEP shapes, 24 is the best
   // of the three on both; Exactdistance: 2 CTAs of 16.  BANG_B200_WARPS_PER_SM overrides (up to 32).
   int max_warps = c->mode == BANG_MODE_EXACTDISTANCE ? 32 : 24;   // measured: profiles/r2_concurrency.md
-  if (const char* e = getenv("BANG_B200_WARPS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) max_warps = v; }
+  bool keep_l1 = true;  // (an explicit warp count is taken as given)
+  if (const char* e = getenv("BANG_B200_WARPS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 64) { max_warps = v; keep_l1 = false; } }
   if (const char* e = getenv("BANG_B200_CODE_PREFETCH")) c->code_prefetch = atoi(e) != 0;
-  if (const char* e = getenv("BANG_B200_ROW_PREFETCH")) c->row_prefetch = atoi(e) != 0;
   // A pivot table that does not fit next to one query's state (256 x D floats: D above ~215) stays in global memory
   // (L2-resident, read with plain loads by the generic-chunk kernel) instead of being refused.
   c->piv_global = false;
-  LaunchGeom g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps, false);
+  LaunchGeom g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps, false, keep_l1);
   if (g.warps_per_cta < 1 && c->mode != BANG_MODE_EXACTDISTANCE) {
     c->piv_global = true;
-    g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps, true);
+    g = geometry_for(c, c->L, max_iter + 1, (size_t)max_optin, (size_t)per_sm, max_warps, true, keep_l1);
   }
   if (g.warps_per_cta < 1)
     return set_err(BANG_E_UNSUPPORTED, "one query's state (D = " + std::to_string(c->D) + ", L = " + std::to_string(c->L) + ") does not fit in " +
@@ -804,7 +803,6 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   a->cand_log = c->d_candlog;
   a->piv_global = c->piv_global ? 1u : 0u;
   a->code_prefetch = c->code_prefetch ? 1u : 0u;
-  a->row_prefetch = c->row_prefetch ? 1u : 0u;
   a->stop_on_empty_hop = c->mode == BANG_MODE_EXACTDISTANCE ? 1u : 0u;  // BANG_Exactdistance/parANN.cu:1593-1671 as built
   a->counter = c->d_counter;
   a->st_hops = c->d_hops;

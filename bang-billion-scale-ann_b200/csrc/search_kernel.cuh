@@ -50,7 +50,7 @@ namespace bang {
 constexpr int kThreads = 32;            // threads per query = one warp (see the header comment)
 constexpr int kMaxWarpsPerCta = 32;  // PQ modes: one CTA of up to 32 query warps per SM (kernels compiled for 16 / 24 / 32, see bang_search_kernel)
 constexpr int kMaxR = 64;               // MAX_R, bang_search.cu:35
-constexpr int kListCap = kMaxR + 4;     // medoid + R neighbours (65), padded so that every list is a multiple of 16 bytes
+constexpr int kListCap = kMaxR + 8;     // medoid + R neighbours (65), padded to whole 16-byte groups (68); the last two id slots hold statistics
 constexpr uint32_t kVisitedBit = 0x80000000u;  // worklist entries carry their visited flag in the top bit of the id word (ids < 2^31, checked at load)
 constexpr uint32_t kBfEntries = 399887u;  // BF_ENTRIES, bang_search.cu:48
 // The visited filter has the reference's semantics — a 399887-slot bit array addressed by two hashes — but is
@@ -106,7 +106,6 @@ struct SearchArgs {
   uint32_t* cand_log;       // device: expanded-node log, cand_cap ids per resident query warp (PQ modes; read back by the re-rank)
   uint32_t piv_global;      // 1: the pivot table stays in global memory (it does not fit in shared memory: D above ~215)
   uint32_t code_prefetch;   // 1: request the PQ codes of every neighbour towards L2 while the filter is consulted
-  uint32_t row_prefetch;    // 1: at the start of a hop, request the row of the closest unexpanded worklist entry towards L2 (the likely next node)
   uint32_t stop_on_empty_hop;  // 1 (Exactdistance searches): a hop without new neighbours ends the query, see the kernel; 0 for the index builder
   uint32_t* counter;        // device work counter (zeroed before launch)
   uint32_t* st_hops;        // device [Q] or null
@@ -357,10 +356,9 @@ struct QState {
   uint2* w;          // worklist [w_cap], sorted by distance: .x = distance bits, .y = id | kVisitedBit if expanded
   uint32_t* n_id;    // [kListCap] filtered neighbours of this hop, unordered
   float* n_d;
-  uint32_t* s_id;    // [kListCap] the admitted ones, sorted by (dist, id)
+  uint32_t* s_id;    // the admitted ones, sorted by (dist, id): compacted and sorted in place, i.e. the same two arrays
   float* s_d;
   float* cd;         // [cand_cap] exact distances of the re-rank (PQ modes; over the dead worklist)
-  uint32_t* cid;     // [cand_cap] the re-rank's copy of the expanded-node log (behind cd)
   uint32_t* cand_id; // [cand_cap] expanded-node log of this warp, in global memory (PQ modes; one store per hop)
   uint64_t pol_stream, pol_keep;  // L2 policies: evict-first (one-touch gathers), evict-last (visited filter)
 };
@@ -389,8 +387,8 @@ __host__ __device__ inline size_t query_block_bytes(int mode, uint32_t piv_row, 
 template <typename T>
 __host__ __device__ inline size_t warp_private_bytes(int mode, uint32_t piv_row, uint32_t vec_units, uint32_t L, uint32_t cand_cap) {
   const size_t qf = query_block_bytes<T>(mode, piv_row, vec_units);
-  size_t walk = align_up(L, 16) * 8 + (size_t)kListCap * 4 * 4;  // worklist (8 bytes per entry) + n_id/n_d/s_id/s_d
-  if (mode != kExact && walk < (size_t)cand_cap * 8) walk = (size_t)cand_cap * 8;  // (never the case for cand_cap <= L + 121)
+  size_t walk = align_up(L, 16) * 8 + (size_t)kListCap * 4 * 2;  // worklist (8 bytes per entry) + n_id/n_d
+  if (mode != kExact && walk < (size_t)cand_cap * 4) walk = (size_t)cand_cap * 4;  // (the re-rank's distances; never the case for cand_cap <= L + 121)
   return align_up(qf + walk, 16);
 }
 
@@ -409,13 +407,12 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
   s.qc_sa = sbase + (uint32_t)o;
   o += query_block_bytes<T>(mode, a.piv_row, a.vec_units);
   s.cd = (float*)(base + o);
-  s.cid = (uint32_t*)(base + o) + a.cand_cap;
   const size_t wcap = align_up(a.L, 16);
   s.w = (uint2*)(base + o); o += wcap * 8;
   s.n_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
-  s.n_d = (float*)(base + o); o += (size_t)kListCap * 4;
-  s.s_id = (uint32_t*)(base + o); o += (size_t)kListCap * 4;
-  s.s_d = (float*)(base + o);
+  s.n_d = (float*)(base + o);
+  s.s_id = s.n_id;
+  s.s_d = s.n_d;
   s.cand_id = a.cand_log ? a.cand_log + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.cand_cap : nullptr;
 }
 
@@ -694,7 +691,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   if (acc1) s.n_id[pre + c0 + __popc(m1 & lt)] = id1;
   {
     const uint32_t deg = __popc(__ballot_sync(kFull, v0)) + __popc(__ballot_sync(kFull, v1));
-    if (lane == 0) { s.n_id[kListCap - 1] += deg; s.s_id[kListCap - 1] += n; }
+    if (lane == 0) { s.n_id[kListCap - 1] += deg; s.n_id[kListCap - 2] += n; }
   }
   __syncwarp();
   pf.tick(PT_COMPACT);
@@ -768,7 +765,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
 __device__ __forceinline__ void write_stats(const SearchArgs& a, const QState& s, uint32_t q) {
   if (s.lane == 0) {
     if (a.st_sumdeg) a.st_sumdeg[q] = s.n_id[kListCap - 1];
-    if (a.st_npass) a.st_npass[q] = s.s_id[kListCap - 1];
+    if (a.st_npass) a.st_npass[q] = s.n_id[kListCap - 2];
   }
   __syncwarp();
 }
@@ -833,9 +830,12 @@ __device__ __forceinline__ void select_admitted(const QState& s, uint32_t n, uin
     uint32_t base = 0;
     for (uint32_t i0 = 0; i0 < n; i0 += 32) {
       const uint32_t i = i0 + lane;
-      const bool in = i < n && s.n_d[i] < maxd;
-      const uint32_t m = __ballot_sync(kFull, in);
-      if (in) { const uint32_t p = base + __popc(m & lt); s.s_d[p] = s.n_d[i]; s.s_id[p] = s.n_id[i]; }
+      float d = 0.0f;
+      uint32_t id = 0;
+      if (i < n) { d = s.n_d[i]; id = s.n_id[i]; }
+      const bool in = i < n && d < maxd;
+      const uint32_t m = __ballot_sync(kFull, in);  // (in place: every lane has read its entry before any lane writes)
+      if (in) { const uint32_t p = base + __popc(m & lt); s.s_d[p] = d; s.s_id[p] = id; }
       base += __popc(m);
     }
     __syncwarp();
@@ -849,13 +849,34 @@ __device__ __forceinline__ void select_admitted(const QState& s, uint32_t n, uin
     __syncwarp();
     if (lane < nb) { s.s_d[r] = __uint_as_float(kd); s.s_id[r] = ki; }
   } else {
-    for (uint32_t i = lane; i < n; i += 32) {
-      const float d = s.n_d[i];
-      const uint32_t id = s.n_id[i];
-      uint32_t r = 0;
-      for (uint32_t j = 0; j < n; ++j) r += key_less(s.n_d[j], s.n_id[j], d, id) ? 1u : 0u;
-      if (r < nb) { s.s_d[r] = d; s.s_id[r] = id; }
+    // rank of every entry among all n by the 64-bit key (distance bits, id) — distances are >= +0, so their bit patterns
+    // order like the floats.  The list is read four entries at a time (16-byte broadcast loads) against the lane's two
+    // entries (i = lane, lane + 32); the tail of the last group of four is padded with +inf keys.
+    if (lane < 3 && n + lane < ((n + 3u) & ~3u)) s.n_d[n + lane] = __uint_as_float(0x7F800000u);
+    __syncwarp();
+    const uint32_t ia = lane, ib = lane + 32;
+    const unsigned long long ka = ia < n ? ((unsigned long long)__float_as_uint(s.n_d[ia]) << 32 | s.n_id[ia]) : ~0ull;
+    const unsigned long long kb = ib < n ? ((unsigned long long)__float_as_uint(s.n_d[ib]) << 32 | s.n_id[ib]) : ~0ull;
+    uint32_t ra = 0, rb = 0;
+    for (uint32_t j0 = 0; j0 < n; j0 += 4) {
+      const uint4 dj = *reinterpret_cast<const uint4*>(s.n_d + j0), ij = *reinterpret_cast<const uint4*>(s.n_id + j0);
+      const unsigned long long k0 = (unsigned long long)dj.x << 32 | ij.x, k1 = (unsigned long long)dj.y << 32 | ij.y;
+      const unsigned long long k2 = (unsigned long long)dj.z << 32 | ij.z, k3 = (unsigned long long)dj.w << 32 | ij.w;
+      ra += (k0 < ka ? 1u : 0u) + (k1 < ka ? 1u : 0u) + (k2 < ka ? 1u : 0u) + (k3 < ka ? 1u : 0u);
+      rb += (k0 < kb ? 1u : 0u) + (k1 < kb ? 1u : 0u) + (k2 < kb ? 1u : 0u) + (k3 < kb ? 1u : 0u);
     }
+    float d64 = 0.0f;
+    uint32_t id64 = 0, r64 = kNone;
+    if (n > 64 && lane == 0) {  // (a 65th entry: the medoid's list on the first hop)
+      d64 = s.n_d[64];
+      id64 = s.n_id[64];
+      r64 = 0;
+      for (uint32_t j = 0; j < n; ++j) r64 += key_less(s.n_d[j], s.n_id[j], d64, id64) ? 1u : 0u;
+    }
+    __syncwarp();  // the sorted list replaces the unsorted one in place: every rank is known before the first store
+    if (ia < n && ra < nb) { s.s_d[ra] = __uint_as_float((uint32_t)(ka >> 32)); s.s_id[ra] = (uint32_t)ka; }
+    if (ib < n && rb < nb) { s.s_d[rb] = __uint_as_float((uint32_t)(kb >> 32)); s.s_id[rb] = (uint32_t)kb; }
+    if (r64 < nb) { s.s_d[r64] = d64; s.s_id[r64] = id64; }
   }
   __syncwarp();
 }
@@ -989,14 +1010,13 @@ template <typename T>
 __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
   const uint32_t lane = s.lane, t = lane & 7, g = lane >> 3;
   float* cd = s.cd;       // the worklist block is dead by now: exact distances + a copy of the log go there,
-  uint32_t* cid = s.cid;  // the fp32 query where query - centroid was (see warp_private_bytes)
+  const uint32_t* cid = s.cand_id;  // the expanded-node log in global memory (L2): ids are re-read from there
   __syncwarp();
   load_query<T>(a, q, s.q_f);
-  for (uint32_t i = lane; i < n; i += 32) cid[i] = __ldcg(s.cand_id + i);
   __syncwarp();
   for (uint32_t b0 = 0; b0 < n; b0 += 8) {
     const uint32_t i0 = b0 + g, i1 = b0 + 4 + g;
-    const uint32_t id0 = i0 < n ? cid[i0] : a.medoid, id1 = i1 < n ? cid[i1] : a.medoid;
+    const uint32_t id0 = i0 < n ? __ldcg(cid + i0) : a.medoid, id1 = i1 < n ? __ldcg(cid + i1) : a.medoid;
     float d0, d1;
     l2_two_rows_8lane<T>(row_ptr(a, id0) + kAdjBytes, row_ptr(a, id1) + kAdjBytes, s.q_f, a.vec_units, t, &d0, &d1);
     if (t == 0 && i0 < n) cd[i0] = d0;
@@ -1008,7 +1028,7 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
   for (uint32_t r = 0; r < a.k; ++r) {
     uint32_t bd = 0xFFFFFFFFu, bid = kNone;
     for (uint32_t i = lane; i < n; i += 32) {
-      const uint32_t db = __float_as_uint(cd[i]), id = cid[i];
+      const uint32_t db = __float_as_uint(cd[i]), id = __ldcg(cid + i);
       const bool after = !have_last || db > last_d || (db == last_d && id > last_id);
       if (after && (db < bd || (db == bd && id < bid))) { bd = db; bid = id; }
     }
@@ -1089,7 +1109,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     pf.tick(PT_SETUP);
 
     uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1, pos0 = 0;
-    if (lane == 0) { s.n_id[kListCap - 1] = 0; s.s_id[kListCap - 1] = 0; }  // statistics (see expand)
+    if (lane == 0) { s.n_id[kListCap - 1] = 0; s.n_id[kListCap - 2] = 0; }  // statistics (see expand)
     auto log_parent = [&](uint32_t node) {
       if (lane == 0) {
         if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
@@ -1154,9 +1174,6 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-        // the closest unexpanded worklist entry is the next node to expand unless this hop finds a closer one: its
-        // adjacency row starts travelling towards L2 now, a whole hop before it is needed
-        if (a.row_prefetch && fu != kNone) prefetch_l2(row_ptr(a, s.w[fu].y) + 8 * lane);
         const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, pf);
         // Exactdistance: a hop whose neighbours are all filtered out ends the query — what the reference's fused
         // kernel does when built for sm_100a (it scans the worklist up to a size it only sets when there are new
@@ -1249,7 +1266,8 @@ struct LaunchGeom { int warps_per_cta; int ctas_per_sm; size_t smem; };
 inline int wpc_variant(int mode, int warps) { return (mode == kExact || warps <= 16) ? 16 : (warps <= 24 ? 24 : 32); }
 template <typename T>
 inline LaunchGeom launch_geometry(int mode, uint32_t piv_row, uint32_t n_chunks, uint32_t vec_units, uint32_t L, uint32_t cand_cap,
-                                  size_t smem_optin_per_block, size_t smem_per_sm, int max_warps_per_sm, bool piv_global = false) {
+                                  size_t smem_optin_per_block, size_t smem_per_sm, int max_warps_per_sm, bool piv_global = false,
+                                  bool keep_l1 = true) {
   const size_t shared = cta_shared_bytes(mode, piv_row, n_chunks, piv_global), per = warp_private_bytes<T>(mode, piv_row, vec_units, L, cand_cap);
   LaunchGeom g{0, 0, 0};
   if (shared + per > smem_optin_per_block) return g;
@@ -1257,6 +1275,14 @@ inline LaunchGeom launch_geometry(int mode, uint32_t piv_row, uint32_t n_chunks,
   const int cap = mode == kExact ? 16 : kMaxWarpsPerCta;
   if (w > cap) w = cap;
   if (max_warps_per_sm > 0 && w > max_warps_per_sm) w = max_warps_per_sm;
+  // Shared memory and L1 share 256 KB per SM and the split moves in steps (... 164, 196, 228 KB of shared memory, 1 KB per
+  // CTA reserved by the system).  The gathers of the traversal are scattered 8..32-byte loads whose lines in flight live
+  // in L1: crossing from the 196 KB step (60 KB of L1) to the 228 KB step (28 KB) costs 15 % on the C2 shape at the same
+  // number of warps (profiles/r2_l1_carveout.md), so the PQ modes give up a few resident queries to stay below the step.
+  if (keep_l1 && mode != kExact) {
+    const size_t step = (size_t)196 * 1024 - 1024;
+    if (shared + (size_t)w * per > step && shared + 16 * per <= step) w = (int)((step - shared) / per);
+  }
   g.warps_per_cta = w;
   g.smem = shared + (size_t)w * per;
   // Exactdistance (no CTA-shared table): several CTAs per SM, bounded by shared memory and the warp budget
