@@ -777,6 +777,8 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   memset(a, 0, sizeof(*a));
   for (int s = 0; s < kMaxShards; ++s) a->rows[s] = c->rows[s];
   a->n_shards = c->n_shards;
+  a->shard_shift = 0;
+  if (c->n_shards > 1 && (c->n_shards & (c->n_shards - 1)) == 0) while ((1u << a->shard_shift) < (uint32_t)c->n_shards) ++a->shard_shift;
   a->row_stride = c->row_stride;
   a->codes = c->d_codes;
   a->code_stride = c->code_stride;
@@ -789,7 +791,7 @@ static void fill_args(const bang_b200_ctx* c, SearchArgs* a, const void* d_queri
   a->chunk_off = c->d_chunk_off;
   a->D = c->D;
   a->vec_units = c->vec_units;
-  a->medoid = (uint32_t)c->medoid;
+  set_medoid(*a, (uint32_t)c->medoid, c->mode == BANG_MODE_EXACTDISTANCE);
   a->L = c->L;
   a->k = c->k;
   a->Q = Q;

@@ -317,7 +317,7 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
 
   SearchArgs a;
   memset(&a, 0, sizeof(a));
-  a.rows[0] = rows; a.n_shards = 1; a.row_stride = row_stride; a.D = D; a.vec_units = vec_units; a.medoid = medoid;
+  a.rows[0] = rows; a.n_shards = 1; a.row_stride = row_stride; a.D = D; a.vec_units = vec_units; set_medoid(a, medoid, true);
   a.L = L; a.k = 1; a.q_dim = D; a.max_iter = max_iter; a.cand_cap = cand_cap; a.queries = d_q; a.out_ids = d_ids; a.out_dists = d_dd;
   a.bloom = d_bloom; a.counter = d_counter; a.dump_ids = d_dump; a.dump_n = d_dump_n; a.dump_stride = cand_cap;
 

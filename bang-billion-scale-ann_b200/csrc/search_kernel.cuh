@@ -80,6 +80,7 @@ struct SearchArgs {
   // ---- index (HBM layout) ----
   const uint8_t* rows[kMaxShards];  // shard s holds ids with id % n_shards == s at local row id / n_shards
   uint32_t n_shards;
+  uint32_t shard_shift;     // log2(n_shards) when n_shards is a power of two above 1, else 0
   uint32_t row_stride;      // bytes, multiple of 32: [ R x u32 adjacency | vector padded to 16 B ]
   const uint8_t* codes;     // [N][code_stride], bytes permuted per 32-chunk group (see repack_codes)
   uint32_t code_stride;
@@ -94,6 +95,7 @@ struct SearchArgs {
   uint32_t D;               // dims of the index
   uint32_t vec_units;       // 16-byte units per vector (D*sizeof(T) rounded up / 16)
   uint32_t medoid;
+  uint32_t med_blk8[2], med_off[2], med_slots;  // the medoid's visited-filter slots (block byte offset, offset in the block), see set_medoid
   // ---- search ----
   uint32_t L, k, Q;
   uint32_t q_dim;           // elements per query row (D, or D-1 for MIPS)
@@ -121,7 +123,7 @@ struct SearchArgs {
 // ------------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t hash1(uint32_t x) {  // hashFn1_d, bang_search.cu:1168-1178
+__host__ __device__ __forceinline__ uint32_t hash1(uint32_t x) {  // hashFn1_d, bang_search.cu:1168-1178
   uint64_t h = 0xcbf29ce4ull;
   h = (h ^ (x & 0xff)) * 0x01000193ull;
   h = (h ^ ((x >> 8) & 0xff)) * 0x01000193ull;
@@ -129,13 +131,21 @@ __device__ __forceinline__ uint32_t hash1(uint32_t x) {  // hashFn1_d, bang_sear
   h = (h ^ ((x >> 24) & 0xff)) * 0x01000193ull;
   return (uint32_t)(h % kBfEntries);
 }
-__device__ __forceinline__ uint32_t hash2(uint32_t x) {  // hashFn2_d, bang_search.cu:1179-1189
+__host__ __device__ __forceinline__ uint32_t hash2(uint32_t x) {  // hashFn2_d, bang_search.cu:1179-1189
   uint64_t h = 0x84222325ull;
   h = (h ^ (x & 0xff)) * 0x1B3ull;
   h = (h ^ ((x >> 8) & 0xff)) * 0x1B3ull;
   h = (h ^ ((x >> 16) & 0xff)) * 0x1B3ull;
   h = (h ^ ((x >> 24) & 0xff)) * 0x1B3ull;
   return (uint32_t)(h % kBfEntries);
+}
+
+// host side: the entry point and its visited-filter slots (a pure function of the id, so computed once per launch here)
+inline void set_medoid(SearchArgs& a, uint32_t medoid, bool one_hash /* Exactdistance */) {
+  a.medoid = medoid;
+  const uint32_t p[2] = {hash1(medoid), hash2(medoid)};
+  for (int h = 0; h < 2; ++h) { a.med_blk8[h] = p[h] / 255u * 8u; a.med_off[h] = p[h] % 255u; }
+  a.med_slots = (one_hash || p[0] == p[1]) ? 1u : 2u;
 }
 
 __device__ __forceinline__ bool key_less(float da, uint32_t ia, float db, uint32_t ib) {
@@ -182,8 +192,10 @@ template <> struct Elem<int8_t> {
 
 __device__ __forceinline__ const uint8_t* row_ptr(const SearchArgs& a, uint32_t id) {
   if (a.n_shards == 1) return a.rows[0] + (size_t)id * a.row_stride;
-  const uint32_t s = id % a.n_shards;
-  return a.rows[s] + (size_t)(id / a.n_shards) * a.row_stride;  // local HBM or a peer mapping over NVLink
+  // local HBM or a peer mapping over NVLink; 2, 4 or 8 shards: mask and shift (shard_shift > 0) instead of a division
+  const uint32_t s = a.shard_shift ? (id & (a.n_shards - 1u)) : id % a.n_shards;
+  const uint32_t r = a.shard_shift ? (id >> a.shard_shift) : id / a.n_shards;
+  return a.rows[s] + (size_t)r * a.row_stride;
 }
 
 // L2 residency control.  The per-query visited filters (25 KB of blocks each, re-read every hop) are the only
@@ -224,50 +236,60 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void* p, uint64_t pol) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ---- sparse visited filter (see kVisBlocks) -------------------------------------------------------
-typedef uint32_t VisAddr;  // (block index << 8) | offset within the block (0..254)
-__device__ __forceinline__ VisAddr vis_addr(uint32_t pos) {
+// A slot is addressed by the byte offset of its 8-byte block from SearchArgs::bloom (32 bits: the filters of a whole
+// grid are a few hundred MB) and its offset inside the block; every access is  bloom + o  — one 64-bit add on a
+// kernel parameter — instead of a pointer rebuilt from the warp's number.
+struct VisSlot { uint32_t o, off; };
+struct VisBase { uint32_t blocks_o, bitmaps_o; };  // byte offsets of this warp's block area / spill-bitmap area from SearchArgs::bloom
+__device__ __forceinline__ VisSlot vis_slot(const VisBase& vb, uint32_t pos) {
   const uint32_t blk = __umulhi(pos, 0x80808081u) >> 7;  // pos / 255 (exact for pos < 2^31)
-  return (blk << 8) | (pos - blk * 255u);
+  VisSlot v;
+  v.off = pos - blk * 255u;
+  v.o = vb.blocks_o + blk * 8u;
+  return v;
 }
-__device__ __forceinline__ uint2 vis_ld_block(const uint8_t* vis, VisAddr a, uint64_t pol_keep) {
+__device__ __forceinline__ uint2 vis_ld_block(const uint8_t* bloom, uint32_t o, uint64_t pol_keep) {
   uint2 r;
-  const uint8_t* p = vis + (size_t)(a >> 8) * 8;
-  asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_keep));
+  asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(bloom + o), "l"(pol_keep));
   return r;
 }
-// is the slot set, given its block?  Bytes 0..6 hold offsets of set slots or 0xFF; byte 7 counts insertions.
-__device__ __forceinline__ bool vis_test(const uint32_t* vbm, uint2 blk, VisAddr a) {
-  const uint32_t pat = (a & 255u) * 0x01010101u;
+// is the slot among the block's (up to 7) offset bytes?  Bytes 0..6 hold offsets of set slots or 0xFF; byte 7 counts insertions.
+__device__ __forceinline__ bool vis_test(uint2 blk, uint32_t off) {
+  const uint32_t pat = off * 0x01010101u;
   // "does any byte equal off": (x - 0x01..) & ~x & 0x80.. is non-zero iff x has a zero byte (exact for the any-test)
   const uint32_t x0 = blk.x ^ pat, x1 = (blk.y ^ pat) | 0xFF000000u;  // byte 7 = count
-  bool found = ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1)) & 0x80808080u) != 0;
-  if (!found && (blk.y >> 24) > kVisSlotsPerBlock) {  // the block spilled: its bitmap holds the 8th and later slots
-    const uint32_t off = a & 255u;
-    found = (__ldcg(vbm + (size_t)(a >> 8) * 8 + (off >> 5)) >> (off & 31u)) & 1u;
-  }
-  return found;
+  return ((((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1)) & 0x80808080u) != 0;
+}
+// a block whose count exceeds 7 spilled: its 255-bit bitmap (in the warp's bitmap area) holds the 8th and later slots
+__device__ __forceinline__ bool vis_block_spilled(uint2 blk) { return blk.y >= ((kVisSlotsPerBlock + 1u) << 24); }
+__device__ __forceinline__ uint32_t* vis_bitmap_word(uint8_t* bloom, const VisBase& vb, const VisSlot& v) {
+  return reinterpret_cast<uint32_t*>(bloom + vb.bitmaps_o + (v.o - vb.blocks_o) * 4u) + (v.off >> 5);
+}
+__device__ __forceinline__ bool vis_test_spilled(uint8_t* bloom, const VisBase& vb, const VisSlot& v) {
+  return (__ldcg(vis_bitmap_word(bloom, vb, v)) >> (v.off & 31u)) & 1u;
 }
 // set a slot (not currently set), in two steps so that nothing waits for the atomic's round trip:
 // vis_reserve bumps the block's count byte with one L2 atomic and returns the old count word; vis_commit, called
 // after the distance computations of the hop, stores the offset byte into the reserved position.  Reservations
 // 7 and up belong to the spill bitmap (vis_spill_*): the one lane that drew number 7 clears the block's bitmap,
 // then, after a warp barrier, every lane with a number >= 7 sets its bit.
-__device__ __forceinline__ uint32_t vis_reserve(uint8_t* vis, VisAddr a) {
-  return atomicAdd(reinterpret_cast<uint32_t*>(vis + (size_t)(a >> 8) * 8 + 4), 1u << 24);
+__device__ __forceinline__ uint32_t vis_reserve(uint8_t* bloom, uint32_t o) {
+  return atomicAdd(reinterpret_cast<uint32_t*>(bloom + o + 4), 1u << 24);
 }
-__device__ __forceinline__ bool vis_commit(uint8_t* vis, uint32_t* vbm, VisAddr a, uint32_t old) {  // true: spilled
-  const uint32_t idx = old >> 24;
-  if (idx < kVisSlotsPerBlock) { vis[(size_t)(a >> 8) * 8 + idx] = (uint8_t)(a & 255u); return false; }
-  if (idx == kVisSlotsPerBlock) {
-    uint4* b = reinterpret_cast<uint4*>(vbm + (size_t)(a >> 8) * 8);
-    b[0] = make_uint4(0u, 0u, 0u, 0u);
-    b[1] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  return true;
+// the same under a predicate (bit `bit` of `mask`), without a branch; 0 when the slot is not inserted
+__device__ __forceinline__ uint32_t vis_reserve_if(uint8_t* bloom, uint32_t o, uint32_t mask, uint32_t bit) {
+  uint32_t r = 0;
+  asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 q, t, 0;\n\t@q atom.global.add.u32 %0, [%1+4], 16777216;\n\t}"
+               : "+r"(r) : "l"(bloom + o), "r"(mask), "r"(bit) : "memory");
+  return r;
 }
-__device__ __forceinline__ void vis_spill_set(uint32_t* vbm, VisAddr a) {
-  const uint32_t off = a & 255u;
-  atomicOr(vbm + (size_t)(a >> 8) * 8 + (off >> 5), 1u << (off & 31u));
+__device__ __forceinline__ void vis_spill_clear(uint8_t* bloom, const VisBase& vb, const VisSlot& v) {
+  uint4* b = reinterpret_cast<uint4*>(bloom + vb.bitmaps_o + (v.o - vb.blocks_o) * 4u);
+  b[0] = make_uint4(0u, 0u, 0u, 0u);
+  b[1] = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void vis_spill_set(uint8_t* bloom, const VisBase& vb, const VisSlot& v) {
+  atomicOr(vis_bitmap_word(bloom, vb, v), 1u << (v.off & 31u));
 }
 
 // Exact squared L2 between one HBM row vector and the query (fp32 copy in shared memory).
@@ -524,6 +546,13 @@ __device__ __forceinline__ float adc4_word(uint32_t pa /* table + 16 t */, uint3
   return __fadd_rn(__fadd_rn(__fadd_rn(e0, e1), e2), e3);
 }
 
+// address of lane t's code word of point `id` (32-byte code rows): one multiply-add on the 64-bit base
+__device__ __forceinline__ const uint8_t* code_row(const uint8_t* cbase, uint32_t id) {
+  const uint8_t* p;
+  asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(p) : "r"(id), "l"(cbase));
+  return p;
+}
+
 template <typename T>
 __device__ __forceinline__ void load_query(const SearchArgs& a, uint32_t q, float* q_f) {
   const T* src = reinterpret_cast<const T*>(a.queries) + (size_t)q * a.q_dim;
@@ -576,25 +605,26 @@ struct Prof {
 };
 #endif
 
-// what one lane has to store into the filter after its reservations: slot addresses, the counts the atomics
-// returned, and a mask (bits 0-3: the lane's own four slots, bits 4-5: the medoid's, first hop, lane 0)
-struct FilterIns { VisAddr a[4]; uint32_t r[4]; VisAddr am[2]; uint32_t rm[2]; uint32_t ins; };
-__device__ __forceinline__ void commit_filter(uint8_t* vis, uint32_t* vbm, const FilterIns& f) {
-  uint32_t spill = 0;
+// what one lane has to store into the filter after its reservations: its four slots, the count words the atomics
+// returned, and a mask of the slots it inserts
+struct FilterIns { VisSlot v[4]; uint32_t r[4]; uint32_t ins; };
+__device__ __forceinline__ void commit_filter(uint8_t* bloom, const VisBase& vb, const FilterIns& f) {
+  bool spill = false;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (f.ins & (1u << i)) spill |= vis_commit(vis, vbm, f.a[i], f.r[i]) ? (1u << i) : 0u;
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-    if (f.ins & (16u << i)) spill |= vis_commit(vis, vbm, f.am[i], f.rm[i]) ? (16u << i) : 0u;
-  if (__any_sync(kFull, spill != 0)) {  // rare: blocks with more than 7 slots
-    __syncwarp();                       // the freshly spilled blocks' bitmaps are cleared
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t idx = f.r[i] >> 24;
+    const bool in = (f.ins >> i) & 1u;
+    if (in && idx < kVisSlotsPerBlock) bloom[f.v[i].o + idx] = (uint8_t)f.v[i].off;
+    spill |= in && idx >= kVisSlotsPerBlock;
+  }
+  if (__any_sync(kFull, spill)) {  // rare: blocks with more than 7 slots
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (spill & (1u << i)) vis_spill_set(vbm, f.a[i]);
+      if (((f.ins >> i) & 1u) && (f.r[i] >> 24) == kVisSlotsPerBlock) vis_spill_clear(bloom, vb, f.v[i]);
+    __syncwarp();                  // the freshly spilled blocks' bitmaps are cleared
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-      if (spill & (16u << i)) vis_spill_set(vbm, f.am[i]);
+    for (int i = 0; i < 4; ++i)
+      if (((f.ins >> i) & 1u) && (f.r[i] >> 24) >= kVisSlotsPerBlock) vis_spill_set(bloom, vb, f.v[i]);
   }
 }
 
@@ -607,23 +637,39 @@ __device__ __forceinline__ VisPos vis_pos(uint32_t id) {
   return p;
 }
 
+// The medoid enters the filter after the tests of the first hop (bang_init seeds it as the first candidate, :455-462; the
+// first list is [medoid] ++ adj(medoid), tested against the empty filter).  One lane, once per query; slots from set_medoid.
+__device__ __forceinline__ void insert_medoid(const SearchArgs& a, uint8_t* bloom, const VisBase& vb) {
+  for (uint32_t h = 0; h < a.med_slots; ++h) {
+    VisSlot v;
+    v.o = vb.blocks_o + a.med_blk8[h];
+    v.off = a.med_off[h];
+    const uint32_t idx = vis_reserve(bloom, v.o) >> 24;
+    if (idx < kVisSlotsPerBlock) { bloom[v.o + idx] = (uint8_t)v.off; continue; }
+    if (idx == kVisSlotsPerBlock) vis_spill_clear(bloom, vb, v);
+    vis_spill_set(bloom, vb, v);
+  }
+}
+
+// per-query statistics, in registers: degrees seen by this lane (summed over the warp at the end), accepted candidates
+struct HopStats { uint32_t deg, npass; };
+
 // ------------------------------------------------------------------------------------------------
 // expansion of one node = stages 4a + 3.  The adjacency row is already in registers (fetch_adj).
 //   filter   neighbor_filtering_new + hashFn1_d/2_d   bang_search.cu:1140-1189 — snapshot semantics: all
 //            tests of a list precede all insertions (the lock-step outcome of the reference's kernel).
-//            On the first hop the filter is empty, so [medoid] ++ adj(medoid) is accepted wholesale.
+//            On the first hop the filter is empty, so [medoid] ++ adj(medoid) is accepted wholesale: the caller
+//            puts the medoid into n_id[0] (pre = 1) and inserts it into the filter afterwards (insert_medoid).
 //   PQ dist  compute_neighborDist_par                 bang_search.cu:1201-1241: lane t of an 8-lane group
 //            owns chunks t, t+8, ... ascending, partials combined by the 8-lane tree.  The HBM code rows
 //            are permuted at load so lane t's chunks 32g+t, 32g+8+t, 32g+16+t, 32g+24+t are one aligned
 //            32-bit word: one 32-byte sector per candidate per 32 chunks, fully used.
 //   exact    compute_neighborDist_par                 BANG_Exactdistance/parANN.cu:1139-1179
-// Returns the number of accepted candidates; n_id/n_d hold them unordered.  The per-query statistics (sum of the
-// expanded nodes' degrees, number of accepted candidates) are kept by lane 0 in the spare last slots of the
-// n_id / s_id lists (a list holds at most 65 entries).
+// Returns the number of accepted candidates (pre included); n_id/n_d hold them unordered.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int MODE, int CS>
-__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* vis, uint32_t* vbm, uint2 nb2, bool first,
-                                           Prof& pf) {
+__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* bloom, const VisBase& vb, uint2 nb2, uint32_t pre,
+                                           HopStats& st, Prof& pf) {
   const uint32_t lane = s.lane, lt = (1u << lane) - 1u;
   const uint32_t id0 = nb2.x, id1 = nb2.y;
   const bool v0 = id0 != kNoNbr, v1 = id1 != kNoNbr;
@@ -635,73 +681,57 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
     if (v0) prefetch_l2(a.codes + (size_t)id0 * a.code_stride);
     if (v1) prefetch_l2(a.codes + (size_t)id1 * a.code_stride);
   }
+  // the four slots of this lane: (id0, hash 1), (id0, hash 2), (id1, hash 1), (id1, hash 2).  A padding id hashes to a
+  // valid slot as well, so the loads and tests need no guard; v0 / v1 enter at the accept decision.
   const VisPos p0 = vis_pos<MODE>(id0), p1 = vis_pos<MODE>(id1);
-  const VisAddr a01 = vis_addr(p0.p1), a02 = vis_addr(p0.p2), a11 = vis_addr(p1.p1), a12 = vis_addr(p1.p2);
+  FilterIns fi;
+  fi.v[0] = vis_slot(vb, p0.p1); fi.v[1] = vis_slot(vb, p0.p2); fi.v[2] = vis_slot(vb, p1.p1); fi.v[3] = vis_slot(vb, p1.p2);
 #ifdef BANG_PHASE_TIMERS
-  if (__any_sync(kFull, a01 == 0xFFFFFFFFu)) printf("");
+  if (__any_sync(kFull, fi.v[0].o == 0xFFFFFFFFu)) printf("");
   pf.tick(PT_HASH);
 #endif
-  // ins bit k: slot k (1 = hash 1, 2 = hash 2) of the id is not set yet and has to be inserted
-  bool acc0 = v0, acc1 = v1;
-  uint32_t ins0 = (MODE == kExact) ? 1u : 3u, ins1 = ins0;
-  if (!first) {
-    bool s01 = false, s02 = false, s11 = false, s12 = false;
-    uint2 b01, b02, b11, b12;
-    if (v0) { b01 = vis_ld_block(vis, a01, s.pol_keep); if (MODE != kExact) b02 = vis_ld_block(vis, a02, s.pol_keep); }
-    if (v1) { b11 = vis_ld_block(vis, a11, s.pol_keep); if (MODE != kExact) b12 = vis_ld_block(vis, a12, s.pol_keep); }
-    if (v0) { s01 = vis_test(vbm, b01, a01); s02 = (MODE == kExact) ? s01 : vis_test(vbm, b02, a02); }
-    if (v1) { s11 = vis_test(vbm, b11, a11); s12 = (MODE == kExact) ? s11 : vis_test(vbm, b12, a12); }
-    acc0 = v0 && !(s01 && s02);
-    acc1 = v1 && !(s11 && s12);
-    ins0 = (s01 ? 0u : 1u) | ((MODE != kExact && !s02) ? 2u : 0u);
-    ins1 = (s11 ? 0u : 1u) | ((MODE != kExact && !s12) ? 2u : 0u);
+  uint32_t nf;  // bit i: slot i is not set in the filter (Exactdistance: bits 0 and 2 only)
+  {
+    const uint2 b01 = vis_ld_block(bloom, fi.v[0].o, s.pol_keep), b11 = vis_ld_block(bloom, fi.v[2].o, s.pol_keep);
+    uint2 b02 = b01, b12 = b11;
+    if (MODE != kExact) { b02 = vis_ld_block(bloom, fi.v[1].o, s.pol_keep); b12 = vis_ld_block(bloom, fi.v[3].o, s.pol_keep); }
+    const bool f01 = vis_test(b01, fi.v[0].off), f11 = vis_test(b11, fi.v[2].off);
+    const bool f02 = MODE == kExact || vis_test(b02, fi.v[1].off), f12 = MODE == kExact || vis_test(b12, fi.v[3].off);
+    const bool sp01 = !f01 && vis_block_spilled(b01), sp02 = !f02 && vis_block_spilled(b02);
+    const bool sp11 = !f11 && vis_block_spilled(b11), sp12 = !f12 && vis_block_spilled(b12);
+    if (__builtin_expect(__any_sync(kFull, sp01 || sp02 || sp11 || sp12), 0)) {  // rare: a block with more than 7 slots, see its bitmap
+      nf = ((f01 || (sp01 && vis_test_spilled(bloom, vb, fi.v[0]))) ? 0u : 1u) | ((f02 || (sp02 && vis_test_spilled(bloom, vb, fi.v[1]))) ? 0u : 2u) |
+           ((f11 || (sp11 && vis_test_spilled(bloom, vb, fi.v[2]))) ? 0u : 4u) | ((f12 || (sp12 && vis_test_spilled(bloom, vb, fi.v[3]))) ? 0u : 8u);
+    } else {
+      nf = (f01 ? 0u : 1u) | (f02 ? 0u : 2u) | (f11 ? 0u : 4u) | (f12 ? 0u : 8u);
+    }
   }
-  if (MODE != kExact) {  // one id whose two hashes coincide sets the slot once
-    if (a01 == a02) ins0 &= 1u;
-    if (a11 == a12) ins1 &= 1u;
+  // an id is accepted unless all its slots are set; its unset slots are inserted (one id whose two hashes coincide sets the slot once)
+  const bool acc0 = v0 && (nf & 3u) != 0, acc1 = v1 && (nf & 12u) != 0;
+  uint32_t ins = (acc0 ? (nf & 3u) : 0u) | (acc1 ? (nf & 12u) : 0u);
+  if (MODE != kExact) {
+    if (p0.p2 == p0.p1) ins &= ~2u;
+    if (p1.p2 == p1.p1) ins &= ~8u;
   }
+  fi.ins = ins;
   __syncwarp();  // every test precedes every insertion
 #ifdef BANG_PHASE_TIMERS
   if (__any_sync(kFull, acc0 && id0 == 0x12345678u)) printf("");
   pf.tick(PT_BLOOM);
 #endif
-  if (!acc0) ins0 = 0;
-  if (!acc1) ins1 = 0;
-  uint32_t r01 = 0, r02 = 0, r11 = 0, r12 = 0, rm1 = 0, rm2 = 0;
-  if (ins0 & 1u) r01 = vis_reserve(vis, a01);
-  if (ins0 & 2u) r02 = vis_reserve(vis, a02);
-  if (ins1 & 1u) r11 = vis_reserve(vis, a11);
-  if (ins1 & 2u) r12 = vis_reserve(vis, a12);
-  uint32_t pre = 0;
-  VisAddr am1 = 0, am2 = 0;
-  if (first) {
-    pre = 1;
-    if (lane == 0) {
-      const VisPos pm = vis_pos<MODE>(a.medoid);
-      am1 = vis_addr(pm.p1); am2 = vis_addr(pm.p2);
-      rm1 = vis_reserve(vis, am1);
-      if (MODE != kExact && am2 != am1) rm2 = vis_reserve(vis, am2);
-      s.n_id[0] = a.medoid;
-    }
-  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) fi.r[i] = vis_reserve_if(bloom, fi.v[i].o, ins, 1u << i);
   const uint32_t m0 = __ballot_sync(kFull, acc0), m1 = __ballot_sync(kFull, acc1);
-  const uint32_t c0 = __popc(m0);
-  const uint32_t n = pre + c0 + __popc(m1);
+  const uint32_t c0 = pre + __popc(m0);
+  const uint32_t n = c0 + __popc(m1);
   if (acc0) s.n_id[pre + __popc(m0 & lt)] = id0;
-  if (acc1) s.n_id[pre + c0 + __popc(m1 & lt)] = id1;
-  {
-    const uint32_t deg = __popc(__ballot_sync(kFull, v0)) + __popc(__ballot_sync(kFull, v1));
-    if (lane == 0) { s.n_id[kListCap - 1] += deg; s.n_id[kListCap - 2] += n; }
-  }
+  if (acc1) s.n_id[c0 + __popc(m1 & lt)] = id1;
+  st.deg += (v0 ? 1u : 0u) + (v1 ? 1u : 0u);
+  st.npass += n;
   __syncwarp();
   pf.tick(PT_COMPACT);
   // The reserved filter bytes are stored after the distance computations of the hop: the atomics that hand out the
   // byte positions have long returned by then, so nothing waits for their round trip.
-  FilterIns fi;
-  fi.a[0] = a01; fi.a[1] = a02; fi.a[2] = a11; fi.a[3] = a12;
-  fi.r[0] = r01; fi.r[1] = r02; fi.r[2] = r11; fi.r[3] = r12;
-  fi.am[0] = am1; fi.am[1] = am2; fi.rm[0] = rm1; fi.rm[1] = rm2;
-  fi.ins = ins0 | (ins1 << 2) | ((first && lane == 0) ? (16u | ((MODE != kExact && am2 != am1) ? 32u : 0u)) : 0u);
   const uint32_t t = lane & 7, g = lane >> 3;  // 4 candidates per pass
   if (MODE == kExact) {
     for (uint32_t k0 = 0; k0 < n; k0 += 8) {  // two rows in flight per lane group
@@ -718,14 +748,18 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
     // candidates (one per 8-lane group) at a time.
     const uint32_t pa = s.piv_sa + 16u * t, qa = s.qc_sa + 16u * t;
     const float4 q0 = lds_f4_off<0>(qa), q1 = lds_f4_off<128>(qa), q2 = lds_f4_off<256>(qa), q3 = lds_f4_off<384>(qa);
-    const uint8_t* cbase = a.codes + 4 * t;  // (32 chunks: 32-byte code rows)
+    const uint8_t* cbase;  // codes + 4 t (32 chunks: 32-byte code rows); opaque, so that it is formed once per hop and not once per load
+    asm volatile("add.u64 %0, %1, %2;" : "=l"(cbase) : "l"(a.codes), "l"((unsigned long long)(4u * t)));
     for (uint32_t k0 = 0; k0 < n; k0 += 16) {
       uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
       const uint32_t kg = k0 + g;
-      if (kg < n) w0 = ld_nc_u32(cbase + (size_t)s.n_id[kg] * 32u, s.pol_stream);
-      if (kg + 4 < n) w1 = ld_nc_u32(cbase + (size_t)s.n_id[kg + 4] * 32u, s.pol_stream);
-      if (kg + 8 < n) w2 = ld_nc_u32(cbase + (size_t)s.n_id[kg + 8] * 32u, s.pol_stream);
-      if (kg + 12 < n) w3 = ld_nc_u32(cbase + (size_t)s.n_id[kg + 12] * 32u, s.pol_stream);
+      // (the four ids are read without a guard: beyond n they are stale entries of the list block, never used)
+      const uint32_t* np = s.n_id + kg;
+      const uint32_t i0 = np[0], i1 = np[4], i2 = np[8], i3 = np[12];
+      if (kg < n) w0 = ld_nc_u32(code_row(cbase, i0), s.pol_stream);
+      if (kg + 4 < n) w1 = ld_nc_u32(code_row(cbase, i1), s.pol_stream);
+      if (kg + 8 < n) w2 = ld_nc_u32(code_row(cbase, i2), s.pol_stream);
+      if (kg + 12 < n) w3 = ld_nc_u32(code_row(cbase, i3), s.pol_stream);
 #ifdef BANG_PHASE_TIMERS
       if (__any_sync(kFull, (w0 ^ w1 ^ w2 ^ w3) == 0x12345678u)) printf("");
       pf.tick(PT_CODEWAIT);
@@ -755,19 +789,18 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       if (t == 0 && k < n) s.n_d[k] = sum;
     }
   }
-  commit_filter(vis, vbm, fi);
+  commit_filter(bloom, vb, fi);
   __syncwarp();
   pf.tick(PT_LUT);
   return n;
 }
 
-// lane 0's statistics (kept in the lists' spare slots, see expand) go to global before the re-rank reuses the block
-__device__ __forceinline__ void write_stats(const SearchArgs& a, const QState& s, uint32_t q) {
+__device__ __forceinline__ void write_stats(const SearchArgs& a, const QState& s, uint32_t q, const HopStats& st) {
+  const uint32_t deg = __reduce_add_sync(kFull, st.deg);
   if (s.lane == 0) {
-    if (a.st_sumdeg) a.st_sumdeg[q] = s.n_id[kListCap - 1];
-    if (a.st_npass) a.st_npass[q] = s.n_id[kListCap - 2];
+    if (a.st_sumdeg) a.st_sumdeg[q] = deg;
+    if (a.st_npass) a.st_npass[q] = st.npass;
   }
-  __syncwarp();
 }
 
 // (dist, id)-minimum of the unsorted neighbour list (optionally skipping the medoid), the number of
@@ -778,20 +811,23 @@ __device__ __forceinline__ Best scan_neighbours(const QState& s, uint32_t n, uin
   const uint32_t lane = s.lane;
   uint32_t bd = 0x7F7FFFFFu /* FLT_MAX */, bid = kNone, below = 0, md = 0;
   bool mi = false;
+  // a list holds at most 65 entries: lane, lane + 32 and (lane 0) entry 64; most hops have fewer than 32
+  auto take = [&](uint32_t i, bool skip) {
+    const float d = s.n_d[i];
+    const uint32_t id = s.n_id[i], db = __float_as_uint(d);
+    below += d < maxd ? 1u : 0u;
+    if (skip && id == medoid) { mi = true; md = db; }
+    else if (db < bd || (db == bd && id < bid)) { bd = db; bid = id; }
+  };
   if (skip_medoid) {  // the first hop: the list starts with the medoid itself, which is not a candidate for expansion
-    for (uint32_t i = lane; i < n; i += 32) {
-      const float d = s.n_d[i];
-      const uint32_t id = s.n_id[i], db = __float_as_uint(d);
-      below += d < maxd ? 1u : 0u;
-      if (id == medoid) { mi = true; md = db; continue; }
-      if (db < bd || (db == bd && id < bid)) { bd = db; bid = id; }
-    }
+    if (lane < n) take(lane, true);
+    if (lane + 32 < n) take(lane + 32, true);
+    if (lane + 64 < n) take(lane + 64, true);
   } else {            // every later hop (med_in / med_d are only read on the first)
-    for (uint32_t i = lane; i < n; i += 32) {
-      const float d = s.n_d[i];
-      const uint32_t id = s.n_id[i], db = __float_as_uint(d);
-      below += d < maxd ? 1u : 0u;
-      if (db < bd || (db == bd && id < bid)) { bd = db; bid = id; }
+    if (lane < n) take(lane, false);
+    if (n > 32) {
+      if (lane + 32 < n) take(lane + 32, false);
+      if (lane + 64 < n) take(lane + 64, false);
     }
   }
   Best b;
@@ -1082,9 +1118,13 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
   s.pol_stream = pol_stream;
   s.pol_keep = l2_policy_evict_last();
   // [block areas of all warps of the grid][spill bitmap areas of all warps of the grid]
-  uint8_t* vis = reinterpret_cast<uint8_t*>(a.bloom) + ((size_t)blockIdx.x * warps + warp) * kVisBlockBytes;
-  uint32_t* vbm = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a.bloom) + (size_t)gridDim.x * warps * kVisBlockBytes +
-                                              ((size_t)blockIdx.x * warps + warp) * kVisBitmapBytes);
+  uint8_t* const bloom = reinterpret_cast<uint8_t*>(a.bloom);
+  VisBase vb;
+  {
+    const uint32_t gw = blockIdx.x * warps + warp;
+    vb.blocks_o = gw * kVisBlockBytes;
+    vb.bitmaps_o = gridDim.x * warps * kVisBlockBytes + gw * kVisBitmapBytes;
+  }
 
   for (;;) {
     uint32_t q = 0;
@@ -1100,7 +1140,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     if (MODE == kExact) load_query<T>(a, q, s.q_f);
     else load_query_residual<T, CS>(a, q, s.qc);
     {  // empty filter: every offset byte 0xFF, count 0 (two 8-byte blocks per store; the padding blocks are never read)
-      uint4* b4 = reinterpret_cast<uint4*>(vis);
+      uint4* b4 = reinterpret_cast<uint4*>(bloom + vb.blocks_o);
       for (uint32_t i = lane; i < (kVisBlocks + 1) / 2; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
     }
     if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
@@ -1109,7 +1149,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     pf.tick(PT_SETUP);
 
     uint32_t ws = 0, fu = kNone, ncand = 1, iter = 1, pos0 = 0;
-    if (lane == 0) { s.n_id[kListCap - 1] = 0; s.n_id[kListCap - 2] = 0; }  // statistics (see expand)
+    HopStats st{0u, 0u};
     auto log_parent = [&](uint32_t node) {
       if (lane == 0) {
         if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
@@ -1120,7 +1160,9 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
 
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
-      uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, true, pf);
+      if (lane == 0) s.n_id[0] = a.medoid;
+      uint32_t n = expand<T, MODE, CS>(a, s, bloom, vb, my_nb, 1u, st, pf);
+      if (lane == 0) insert_medoid(a, bloom, vb);
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
       uint32_t parent = b.id, mark = have ? b.id : 0x01010101u;
@@ -1141,7 +1183,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         pf.tick(PT_UNVIS);
         pf.count(PT_HOPS);
         n = 0;
-        if (have) n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, false, pf);
+        if (have) n = expand<T, MODE, CS>(a, s, bloom, vb, my_nb, 0u, st, pf);
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? w_dist(s, ws - 1) : 0.0f;
@@ -1163,7 +1205,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         pend_nb = n ? admit_count(b.below, n, ws, a.L) : 0u;
         if (iter == a.max_iter - 1) break;
       }
-      write_stats(a, s, q);
+      write_stats(a, s, q, st);
       pf.tick(PT_DECIDE);
       rerank_and_write<T>(a, s, q, ncand);
       pf.tick(PT_RERANK);
@@ -1174,7 +1216,9 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       uint32_t parent = a.medoid;
       for (;;) {
         const bool first = iter == 1;
-        const uint32_t n = expand<T, MODE, CS>(a, s, vis, vbm, my_nb, first, pf);
+        if (first && lane == 0) s.n_id[0] = a.medoid;
+        const uint32_t n = expand<T, MODE, CS>(a, s, bloom, vb, my_nb, first ? 1u : 0u, st, pf);
+        if (first && lane == 0) insert_medoid(a, bloom, vb);
         // Exactdistance: a hop whose neighbours are all filtered out ends the query — what the reference's fused
         // kernel does when built for sm_100a (it scans the worklist up to a size it only sets when there are new
         // neighbours, BANG_Exactdistance/parANN.cu:1593,1600,1671; pinned by tests/golden/ref_forks_golden.npz).
@@ -1219,7 +1263,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         if (capped) break;
         ++iter;
       }
-      write_stats(a, s, q);
+      write_stats(a, s, q, st);
       if (MODE == kExact) {
         // top-k = head of the worklist (Exact parANN.cu:1273-1276)
         __syncwarp();
