@@ -50,7 +50,8 @@ class BangError(RuntimeError):
 class Info(ctypes.Structure):
     _fields_ = [("N", ctypes.c_uint64), ("medoid", ctypes.c_uint64), ("entry_len", ctypes.c_uint64),
                 ("D", ctypes.c_uint32), ("R", ctypes.c_uint32), ("n_chunks", ctypes.c_uint32),
-                ("dtype", ctypes.c_int32), ("mode", ctypes.c_int32), ("device_bytes", ctypes.c_uint64)]
+                ("dtype", ctypes.c_int32), ("mode", ctypes.c_int32), ("device_bytes", ctypes.c_uint64),
+                ("row_stride", ctypes.c_uint32), ("slot_block", ctypes.c_uint32)]
 
 
 class Timing(ctypes.Structure):

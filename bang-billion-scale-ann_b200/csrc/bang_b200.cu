@@ -44,9 +44,16 @@ __device__ __forceinline__ void validate_row(uint32_t ida, uint32_t idb, uint64_
   if (__any_sync(0xffffffffu, dup) && lane == 0) atomicAdd(bad + 2, 1ull);
 }
 
+// the slot block of a row (search_kernel.cuh kSlotBytes): neighbour i's two visited-filter slots as two words at 256 + 8 i
+__device__ __forceinline__ void write_slot_pair(uint8_t* row, uint32_t i, uint32_t id) {
+  uint2 w = make_uint2(0u, 0u);  // (an unused neighbour slot: any valid slot, never accepted)
+  if (id != kNoNbr) w = make_uint2(vis_slot_word(hash1(id)), vis_slot_word(hash2(id)));
+  reinterpret_cast<uint2*>(row + kAdjBytes)[i] = w;
+}
+
 __global__ void repack_rows_kernel(const uint8_t* __restrict__ src, uint64_t entry_len, uint32_t vec_bytes, uint32_t R,
                                    uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t first_id, uint64_t n_ids,
-                                   uint32_t shard, uint32_t n_shards, uint64_t N, unsigned long long* __restrict__ bad) {
+                                   uint32_t shard, uint32_t n_shards, uint64_t N, unsigned long long* __restrict__ bad, uint32_t slot_block) {
   // one warp per node
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -70,10 +77,12 @@ __global__ void repack_rows_kernel(const uint8_t* __restrict__ src, uint64_t ent
       for (int b = 0; b < 4; ++b) v |= (uint32_t)e[vec_bytes + 4 + 4 * i + b] << (8 * b);
     }
     reinterpret_cast<uint32_t*>(d)[i] = v;
+    if (slot_block) write_slot_pair(d, i, v);
     ids[h] = v;
   }
   validate_row(ids[0], ids[1], N, bad);
-  for (uint32_t i = lane; i < row_stride - kAdjBytes; i += 32) d[kAdjBytes + i] = i < vec_bytes ? e[i] : (uint8_t)0;
+  const uint32_t vo = kAdjBytes + (slot_block ? kSlotBytes : 0);
+  for (uint32_t i = lane; i < row_stride - vo; i += 32) d[vo + i] = i < vec_bytes ? e[i] : (uint8_t)0;
 }
 
 // PQ code row [m] -> permuted row [code_stride]: byte (32g + 4t + b) = chunk (32g + 8b + t)
@@ -105,7 +114,7 @@ __global__ void repack_codes_at_kernel(const uint8_t* __restrict__ src, uint32_t
 // device arrays -> HBM rows (bang_b200_load_device_rows): one warp per node
 __global__ void pack_rows_kernel(const uint8_t* __restrict__ vec, uint32_t vec_bytes, const uint32_t* __restrict__ adj,
                                  uint8_t* __restrict__ dst, uint32_t row_stride, uint64_t n, uint64_t N,
-                                 unsigned long long* __restrict__ bad) {
+                                 unsigned long long* __restrict__ bad, uint32_t slot_block) {
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (warp >= n) return;
@@ -113,8 +122,10 @@ __global__ void pack_rows_kernel(const uint8_t* __restrict__ vec, uint32_t vec_b
   const uint32_t ida = adj[warp * kMaxR + lane], idb = adj[warp * kMaxR + 32 + lane];
   reinterpret_cast<uint32_t*>(d)[lane] = ida;
   reinterpret_cast<uint32_t*>(d)[32 + lane] = idb;
+  if (slot_block) { write_slot_pair(d, lane, ida); write_slot_pair(d, 32 + lane, idb); }
   validate_row(ida, idb, N, bad);
-  for (uint32_t i = lane; i < row_stride - kAdjBytes; i += 32) d[kAdjBytes + i] = i < vec_bytes ? vec[warp * vec_bytes + i] : (uint8_t)0;
+  const uint32_t vo = kAdjBytes + (slot_block ? kSlotBytes : 0);
+  for (uint32_t i = lane; i < row_stride - vo; i += 32) d[vo + i] = i < vec_bytes ? vec[warp * vec_bytes + i] : (uint8_t)0;
 }
 
 }  // namespace bang
@@ -157,6 +168,7 @@ struct bang_b200_ctx {
   unsigned long long* d_bad = nullptr;  // row validation counters: degree > R, id >= N, duplicate id (see validate_row)
   bool piv_global = false;              // the pivot table does not fit in shared memory: read it from global/L2
   bool code_prefetch = true;            // speculative L2 prefetch of every neighbour's PQ code row (BANG_B200_CODE_PREFETCH)
+  bool prehash = false;                 // rows carry their neighbours' visited-filter slots (kSlotBytes; decided at load, see set_row_geometry)
   // params
   int k = 0, L = 0, distfn = BANG_DIST_L2, dists_layout = BANG_DISTS_RANK_MAJOR;
   // per-alloc scratch
@@ -187,12 +199,12 @@ static size_t elem_size(int dtype) { return dtype == BANG_DT_FLOAT ? 4 : 1; }
 // ------------------------------------------------------------------------------------------------
 // The search kernels are instantiated per element type in search_inst_{u8,i8,f32}.cu (compiled in parallel); each
 // of those files exports one lookup function (search_inst.cuh).
-static search_fn_t pick_kernel(int dtype, int mode, uint32_t cs, int warps_per_cta) {
+static search_fn_t pick_kernel(int dtype, int mode, uint32_t cs, int warps_per_cta, bool ph) {
   const int wpc = wpc_variant(mode, warps_per_cta);
   switch (dtype) {
-    case BANG_DT_FLOAT: return search_kernel_f32(mode, cs, wpc);
-    case BANG_DT_INT8: return search_kernel_i8(mode, cs, wpc);
-    default: return search_kernel_u8(mode, cs, wpc);
+    case BANG_DT_FLOAT: return search_kernel_f32(mode, cs, wpc, ph);
+    case BANG_DT_INT8: return search_kernel_i8(mode, cs, wpc, ph);
+    default: return search_kernel_u8(mode, cs, wpc, ph);
   }
 }
 static table_fn_t pick_table_kernel(int dtype) {
@@ -339,16 +351,38 @@ static int rows_check_end(bang_b200_ctx* c) {
   return BANG_OK;
 }
 
+// Row geometry.  PQ modes with 32 uniform chunks (the CS = 4 kernels) store, next to the 64 neighbour ids, the two
+// visited-filter slots of every neighbour (512 bytes per row) when the device has room for it: the kernel then reads
+// them with the adjacency instead of evaluating two 64-bit hashes + modulus per neighbour (13 % of a hop's
+// instructions).  BANG_B200_PREHASH=0 / 1 forces the choice; the default is on for an unsharded index whose enlarged
+// rows leave 8 GB of the device free (ranks of a sharded index would all have to take the same decision, and 10^9
+// points do not have the room anyway).  Call after the PQ tables are uploaded (chunk4) and the codes allocated.
+static void set_row_geometry(bang_b200_ctx* c) {
+  c->vec_bytes = c->D * (uint32_t)elem_size(c->dtype);
+  c->vec_units = (c->vec_bytes + 15) / 16;
+  c->rows_local = (c->N + c->n_shards - 1 - c->shard) / c->n_shards;
+  const uint32_t plain = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
+  const uint32_t wide = (uint32_t)align_up(kAdjBytes + kSlotBytes + (size_t)c->vec_units * 16, 32);
+  bool want = c->mode != BANG_MODE_EXACTDISTANCE && c->chunk4 != 0;
+  if (want) {
+    const char* e = getenv("BANG_B200_PREHASH");
+    if (e) want = atoi(e) != 0;
+    else {
+      size_t free_b = 0, total_b = 0;
+      want = c->n_shards == 1 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (size_t)c->rows_local * wide + (8ull << 30) <= free_b;
+    }
+  }
+  c->prehash = want;
+  c->row_stride = want ? wide : plain;
+}
+
 static int load_graph(bang_b200_ctx* c, const std::string& disk_path) {
   uint64_t sz = 0;
   if (!file_size(disk_path, &sz, &g_err)) return BANG_E_IO;
   if (sz != c->N * c->entry_len)
     return set_err(BANG_E_FORMAT, "Graph Index File size " + std::to_string(sz) + " != N*entry_len " +
                                       std::to_string(c->N * c->entry_len));
-  c->vec_bytes = c->D * (uint32_t)elem_size(c->dtype);
-  c->vec_units = (c->vec_bytes + 15) / 16;
-  c->row_stride = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
-  c->rows_local = (c->N + c->n_shards - 1 - c->shard) / c->n_shards;
+  set_row_geometry(c);
   const size_t bytes = (size_t)c->rows_local * c->row_stride;
   {
     std::string why;
@@ -365,7 +399,7 @@ static int load_graph(bang_b200_ctx* c, const std::string& disk_path) {
   rc = stream_file(disk_path, 0, c->entry_len, c->N, [cc](uint8_t* d_chunk, uint64_t first, uint64_t n) -> int {
     const uint64_t threads = n * 32;
     repack_rows_kernel<<<(unsigned)((threads + 255) / 256), 256>>>(d_chunk, cc->entry_len, cc->vec_bytes, cc->R, cc->d_rows,
-                                                                   cc->row_stride, first, n, cc->shard, cc->n_shards, cc->N, cc->d_bad);
+                                                                   cc->row_stride, first, n, cc->shard, cc->n_shards, cc->N, cc->d_bad, cc->prehash ? 1u : 0u);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? BANG_OK : set_err(BANG_E_CUDA, std::string("repack_rows: ") + cudaGetErrorString(e));
   });
@@ -500,10 +534,7 @@ extern "C" int bang_b200_load_device_begin(bang_handle_t c, uint64_t N, uint32_t
     }
     if (rc != BANG_OK) { std::string k = g_err; bang_b200_unload(c); g_err = k; return rc; }
   }
-  c->vec_bytes = D * (uint32_t)elem_size(c->dtype);
-  c->vec_units = (c->vec_bytes + 15) / 16;
-  c->row_stride = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
-  c->rows_local = (N + c->n_shards - 1 - c->shard) / c->n_shards;
+  set_row_geometry(c);
   const size_t bytes = (size_t)c->rows_local * c->row_stride;
   {
     std::string why;
@@ -529,7 +560,7 @@ extern "C" int bang_b200_load_device_rows(bang_handle_t c, uint64_t first_local_
   const uint64_t threads = n_rows * 32;
   pack_rows_kernel<<<(unsigned)((threads + 255) / 256), 256>>>((const uint8_t*)d_vectors, c->vec_bytes, d_adj,
                                                              c->d_rows + first_local_row * c->row_stride, c->row_stride, n_rows,
-                                                             c->N, c->d_bad);
+                                                             c->N, c->d_bad, c->prehash ? 1u : 0u);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaDeviceSynchronize());
   return BANG_OK;
@@ -638,6 +669,7 @@ extern "C" int bang_b200_info(bang_handle_t c, bang_b200_info_t* out) {
   out->N = c->N; out->medoid = c->medoid; out->entry_len = c->entry_len;
   out->D = c->D; out->R = c->R; out->n_chunks = c->n_chunks;
   out->dtype = c->dtype; out->mode = c->mode; out->device_bytes = c->device_bytes;
+  out->row_stride = c->row_stride; out->slot_block = c->prehash ? 1u : 0u;
   return BANG_OK;
 }
 
@@ -686,7 +718,7 @@ static int alloc_impl(bang_b200_ctx* c, int Q) {
   if (g.warps_per_cta < 1)
     return set_err(BANG_E_UNSUPPORTED, "one query's state (D = " + std::to_string(c->D) + ", L = " + std::to_string(c->L) + ") does not fit in " +
                                            std::to_string(max_optin) + " B of shared memory");
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, (c->piv_global || !c->chunk4) ? 0 : 4, g.warps_per_cta);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, (c->piv_global || !c->chunk4) ? 0 : 4, g.warps_per_cta, c->prehash);
   c->smem = g.smem;
   c->warps_per_cta = g.warps_per_cta;
   CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
@@ -820,7 +852,7 @@ static int launch_search(bang_b200_ctx* c, const void* d_queries, int Q, uint64_
   if (c->busy) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_busy, 0));
   CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 4, st));
   const int grid = std::min((Q + c->warps_per_cta - 1) / c->warps_per_cta, c->grid);
-  search_fn_t fn = pick_kernel(c->dtype, c->mode, (c->piv_global || !c->chunk4) ? 0 : 4, c->warps_per_cta);
+  search_fn_t fn = pick_kernel(c->dtype, c->mode, (c->piv_global || !c->chunk4) ? 0 : 4, c->warps_per_cta, c->prehash);
   fn<<<grid, c->warps_per_cta * 32, c->smem, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c->ev_busy, st));

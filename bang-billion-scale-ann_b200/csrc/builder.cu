@@ -281,7 +281,7 @@ int build_impl(const void* d_vectors, uint64_t N, uint32_t D, uint32_t L, float 
   const uint32_t MB = max_batch;
   // search scratch
   // the Exactdistance instantiation of the search kernel (search_inst_*.cu)
-  search_fn_t kern = sizeof(T) == 4 ? search_kernel_f32(kExact, 0, 16) : (std::is_signed<T>::value ? search_kernel_i8(kExact, 0, 16) : search_kernel_u8(kExact, 0, 16));
+  search_fn_t kern = sizeof(T) == 4 ? search_kernel_f32(kExact, 0, 16, false) : (std::is_signed<T>::value ? search_kernel_i8(kExact, 0, 16, false) : search_kernel_u8(kExact, 0, 16, false));
   int max_optin = 0, per_sm = 0;
   B_TRY(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   B_TRY(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));

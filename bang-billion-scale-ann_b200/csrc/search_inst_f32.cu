@@ -3,6 +3,6 @@
 #include "search_inst.cuh"
 
 namespace bang {
-search_fn_t search_kernel_f32(int mode, uint32_t cs, int wpc) { return inst_lookup<float>(mode, cs, wpc); }
+search_fn_t search_kernel_f32(int mode, uint32_t cs, int wpc, bool ph) { return inst_lookup<float>(mode, cs, wpc, ph); }
 table_fn_t table_kernel_f32() { return pq_table_kernel<float>; }
 }  // namespace bang

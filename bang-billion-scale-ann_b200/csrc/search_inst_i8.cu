@@ -3,6 +3,6 @@
 #include "search_inst.cuh"
 
 namespace bang {
-search_fn_t search_kernel_i8(int mode, uint32_t cs, int wpc) { return inst_lookup<int8_t>(mode, cs, wpc); }
+search_fn_t search_kernel_i8(int mode, uint32_t cs, int wpc, bool ph) { return inst_lookup<int8_t>(mode, cs, wpc, ph); }
 table_fn_t table_kernel_i8() { return pq_table_kernel<int8_t>; }
 }  // namespace bang

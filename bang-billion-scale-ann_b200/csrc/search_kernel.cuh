@@ -71,6 +71,12 @@ constexpr uint32_t kVisBitmapBytes = ((kVisBlocks * 32u + 127u) / 128u) * 128u; 
 constexpr uint32_t kBloomWords = (kVisBlockBytes + kVisBitmapBytes) / 4u;
 constexpr uint32_t kNoNbr = 0xFFFFFFFFu;  // padding id in the HBM adjacency rows
 constexpr int kAdjBytes = kMaxR * 4;    // 256 B adjacency block at the head of each HBM row
+// Optional second block (PQ modes, `PH` kernels): the two visited-filter slots of every neighbour, precomputed at load —
+// they are a pure function of the neighbour's id (hashFn1_d / hashFn2_d, bang_search.cu:1168-1189), and evaluating the two
+// 64-bit hashes + the modulus per neighbour is 13 % of a hop's instructions.  8 bytes per neighbour: two words
+// (block byte offset | offset in the block << 24), see vis_slot_word.  A byte-for-instruction trade: the row grows by 512 B.
+constexpr int kSlotBytes = kMaxR * 8;
+template <bool PH> __host__ __device__ constexpr int adj_bytes() { return PH ? kAdjBytes + kSlotBytes : kAdjBytes; }
 constexpr int kMaxShards = 8;
 #define BANG_B200_KERNEL_MAX_L 512  // MAX_L, bang.h:20
 
@@ -248,6 +254,14 @@ __device__ __forceinline__ VisSlot vis_slot(const VisBase& vb, uint32_t pos) {
   v.o = vb.blocks_o + blk * 8u;
   return v;
 }
+// the precomputed form of a slot (rows with the slot block): block byte offset in the low half, offset in the block in the top byte
+__host__ __device__ __forceinline__ uint32_t vis_slot_word(uint32_t pos) { return (pos / 255u * 8u) | ((pos % 255u) << 24); }
+__device__ __forceinline__ VisSlot vis_slot_from_word(const VisBase& vb, uint32_t w) {
+  VisSlot v;
+  v.off = w >> 24;
+  v.o = vb.blocks_o + (w & 0xFFFFu);
+  return v;
+}
 __device__ __forceinline__ uint2 vis_ld_block(const uint8_t* bloom, uint32_t o, uint64_t pol_keep) {
   uint2 r;
   asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(bloom + o), "l"(pol_keep));
@@ -381,7 +395,7 @@ struct QState {
   uint32_t* s_id;    // the admitted ones, sorted by (dist, id): compacted and sorted in place, i.e. the same two arrays
   float* s_d;
   float* cd;         // [cand_cap] exact distances of the re-rank (PQ modes; over the dead worklist)
-  uint32_t* cand_id; // [cand_cap] expanded-node log of this warp, in global memory (PQ modes; one store per hop)
+  uint32_t cand_o;   // expanded-node log of this warp: SearchArgs::cand_log + cand_o, [cand_cap] ids in global memory (PQ modes; one store per hop)
   uint64_t pol_stream, pol_keep;  // L2 policies: evict-first (one-touch gathers), evict-last (visited filter)
 };
 
@@ -435,7 +449,7 @@ __device__ __forceinline__ void carve(QState& s, uint8_t* base, int mode, const 
   s.n_d = (float*)(base + o);
   s.s_id = s.n_id;
   s.s_d = s.n_d;
-  s.cand_id = a.cand_log ? a.cand_log + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.cand_cap : nullptr;
+  s.cand_o = (blockIdx.x * (blockDim.x >> 5) + warp) * a.cand_cap;  // (a few thousand warps x a few hundred entries)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,12 +588,18 @@ __device__ __forceinline__ void load_query_residual(const SearchArgs& a, uint32_
   for (uint32_t j = threadIdx.x & 31; j < a.D; j += 32) qc[j] = __fsub_rn(j < a.q_dim ? (float)src[j] : 0.0f, __ldg(a.centroid + j));
 }
 
-// adjacency prefetch: lane l requests neighbour slots 2l and 2l+1 of `node`'s HBM row (one 256-byte request)
-__device__ __forceinline__ uint2 fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream, uint32_t lane) {
-  uint2 r;
+// adjacency prefetch: lane l requests neighbours 2l and 2l+1 of `node`'s HBM row (one 256-byte request per warp) and, from rows
+// that carry them, the four filter-slot words of the two (one 512-byte request)
+template <bool PH> struct Adj;
+template <> struct Adj<false> { uint2 ids; };
+template <> struct Adj<true> { uint2 ids; uint4 slots; };
+template <bool PH>
+__device__ __forceinline__ Adj<PH> fetch_adj(const SearchArgs& a, uint32_t node, uint64_t pol_stream, uint32_t lane) {
+  Adj<PH> r;
   const uint8_t* p = row_ptr(a, node) + 8 * lane;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
-               : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol_stream));
+               : "=r"(r.ids.x), "=r"(r.ids.y) : "l"(p), "l"(pol_stream));
+  if constexpr (PH) r.slots = ld_nc_u4(p + kAdjBytes + 8 * lane, pol_stream);
   return r;
 }
 
@@ -667,11 +687,11 @@ struct HopStats { uint32_t deg, npass; };
 //   exact    compute_neighborDist_par                 BANG_Exactdistance/parANN.cu:1139-1179
 // Returns the number of accepted candidates (pre included); n_id/n_d hold them unordered.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int MODE, int CS>
-__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* bloom, const VisBase& vb, uint2 nb2, uint32_t pre,
+template <typename T, int MODE, int CS, bool PH>
+__device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s, uint8_t* bloom, const VisBase& vb, const Adj<PH>& nb, uint32_t pre,
                                            HopStats& st, Prof& pf) {
   const uint32_t lane = s.lane, lt = (1u << lane) - 1u;
-  const uint32_t id0 = nb2.x, id1 = nb2.y;
+  const uint32_t id0 = nb.ids.x, id1 = nb.ids.y;
   const bool v0 = id0 != kNoNbr, v1 = id1 != kNoNbr;
 #ifdef BANG_PHASE_TIMERS
   if (__any_sync(kFull, id0 == 0x12345678u && id1 == 0x9abcdef0u)) printf("");  // forces the adjacency load to complete here
@@ -683,9 +703,17 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   }
   // the four slots of this lane: (id0, hash 1), (id0, hash 2), (id1, hash 1), (id1, hash 2).  A padding id hashes to a
   // valid slot as well, so the loads and tests need no guard; v0 / v1 enter at the accept decision.
-  const VisPos p0 = vis_pos<MODE>(id0), p1 = vis_pos<MODE>(id1);
   FilterIns fi;
-  fi.v[0] = vis_slot(vb, p0.p1); fi.v[1] = vis_slot(vb, p0.p2); fi.v[2] = vis_slot(vb, p1.p1); fi.v[3] = vis_slot(vb, p1.p2);
+  bool same0, same1;  // the id's two hashes name one slot
+  if constexpr (PH) {
+    fi.v[0] = vis_slot_from_word(vb, nb.slots.x); fi.v[1] = vis_slot_from_word(vb, nb.slots.y);
+    fi.v[2] = vis_slot_from_word(vb, nb.slots.z); fi.v[3] = vis_slot_from_word(vb, nb.slots.w);
+    same0 = nb.slots.x == nb.slots.y; same1 = nb.slots.z == nb.slots.w;
+  } else {
+    const VisPos p0 = vis_pos<MODE>(id0), p1 = vis_pos<MODE>(id1);
+    fi.v[0] = vis_slot(vb, p0.p1); fi.v[1] = vis_slot(vb, p0.p2); fi.v[2] = vis_slot(vb, p1.p1); fi.v[3] = vis_slot(vb, p1.p2);
+    same0 = p0.p2 == p0.p1; same1 = p1.p2 == p1.p1;
+  }
 #ifdef BANG_PHASE_TIMERS
   if (__any_sync(kFull, fi.v[0].o == 0xFFFFFFFFu)) printf("");
   pf.tick(PT_HASH);
@@ -710,8 +738,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   const bool acc0 = v0 && (nf & 3u) != 0, acc1 = v1 && (nf & 12u) != 0;
   uint32_t ins = (acc0 ? (nf & 3u) : 0u) | (acc1 ? (nf & 12u) : 0u);
   if (MODE != kExact) {
-    if (p0.p2 == p0.p1) ins &= ~2u;
-    if (p1.p2 == p1.p1) ins &= ~8u;
+    if (same0) ins &= ~2u;
+    if (same1) ins &= ~8u;
   }
   fi.ins = ins;
   __syncwarp();  // every test precedes every insertion
@@ -738,7 +766,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
       const uint32_t ka = k0 + g, kb = k0 + 4 + g;
       const uint32_t ca = ka < n ? s.n_id[ka] : a.medoid, cb = kb < n ? s.n_id[kb] : a.medoid;
       float da, db;
-      l2_two_rows_8lane<T>(row_ptr(a, ca) + kAdjBytes, row_ptr(a, cb) + kAdjBytes, s.q_f, a.vec_units, t, &da, &db);
+      l2_two_rows_8lane<T>(row_ptr(a, ca) + adj_bytes<PH>(), row_ptr(a, cb) + adj_bytes<PH>(), s.q_f, a.vec_units, t, &da, &db);
       if (t == 0 && ka < n) s.n_d[ka] = da;
       if (t == 0 && kb < n) s.n_d[kb] = db;
     }
@@ -1042,11 +1070,11 @@ __device__ __forceinline__ uint32_t merge_worklist(const SearchArgs& a, const QS
 // coalesced 16-byte loads, 8 lanes per row, two rows in flight per lane group; then the k smallest by
 // (exact distance, id) (compute_NearestNeighbours, :1312-1368) by k rounds of warp-wide min extraction.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool PH>
 __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QState& s, uint32_t q, uint32_t n) {
   const uint32_t lane = s.lane, t = lane & 7, g = lane >> 3;
   float* cd = s.cd;       // the worklist block is dead by now: exact distances + a copy of the log go there,
-  const uint32_t* cid = s.cand_id;  // the expanded-node log in global memory (L2): ids are re-read from there
+  const uint32_t* cid = a.cand_log + s.cand_o;  // the expanded-node log in global memory (L2): ids are re-read from there
   __syncwarp();
   load_query<T>(a, q, s.q_f);
   __syncwarp();
@@ -1054,7 +1082,7 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
     const uint32_t i0 = b0 + g, i1 = b0 + 4 + g;
     const uint32_t id0 = i0 < n ? __ldcg(cid + i0) : a.medoid, id1 = i1 < n ? __ldcg(cid + i1) : a.medoid;
     float d0, d1;
-    l2_two_rows_8lane<T>(row_ptr(a, id0) + kAdjBytes, row_ptr(a, id1) + kAdjBytes, s.q_f, a.vec_units, t, &d0, &d1);
+    l2_two_rows_8lane<T>(row_ptr(a, id0) + adj_bytes<PH>(), row_ptr(a, id1) + adj_bytes<PH>(), s.q_f, a.vec_units, t, &d0, &d1);
     if (t == 0 && i0 < n) cd[i0] = d0;
     if (t == 0 && i1 < n) cd[i1] = d1;
   }
@@ -1090,7 +1118,7 @@ __device__ __forceinline__ void rerank_and_write(const SearchArgs& a, const QSta
 // the host runs as many warps as shared memory allows for the index's D and the search's L (launch_geometry),
 // because the search is a chain of dependent memory round trips and throughput follows the number of resident
 // queries (profiles/r1_concurrency.md, r2_concurrency.md).  Exactdistance: 2 CTAs of 16 warps per SM.
-template <typename T, int MODE, int CS, int WPC>
+template <typename T, int MODE, int CS, int WPC, bool PH = false>
 __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t warps = blockDim.x >> 5;
@@ -1135,7 +1163,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     Prof pf;
     pf.start();
     // ---- per-query setup: query -> smem, bloom filter cleared ----
-    uint2 my_nb = fetch_adj(a, a.medoid, pol_stream, lane);  // the first hop's adjacency row travels during the setup
+    Adj<PH> my_nb = fetch_adj<PH>(a, a.medoid, pol_stream, lane);  // the first hop's adjacency row travels during the setup
     __syncwarp();
     if (MODE == kExact) load_query<T>(a, q, s.q_f);
     else load_query_residual<T, CS>(a, q, s.qc);
@@ -1143,7 +1171,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       uint4* b4 = reinterpret_cast<uint4*>(bloom + vb.blocks_o);
       for (uint32_t i = lane; i < (kVisBlocks + 1) / 2; i += 32) b4[i] = make_uint4(0xFFFFFFFFu, 0x00FFFFFFu, 0xFFFFFFFFu, 0x00FFFFFFu);
     }
-    if (MODE != kExact && lane == 0) s.cand_id[0] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
+    if (MODE != kExact && lane == 0) a.cand_log[s.cand_o] = a.medoid;  // bang_init: the medoid is every query's first candidate (:455-462)
     __syncwarp();
     __threadfence_block();  // the cleared filter is ordered before this query's tests and insertions
     pf.tick(PT_SETUP);
@@ -1152,7 +1180,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     HopStats st{0u, 0u};
     auto log_parent = [&](uint32_t node) {
       if (lane == 0) {
-        if (MODE != kExact && ncand < a.cand_cap) s.cand_id[ncand] = node;
+        if (MODE != kExact && ncand < a.cand_cap) a.cand_log[s.cand_o + ncand] = node;
         if (MODE == kExact && a.dump_ids && ncand < a.dump_stride) a.dump_ids[(size_t)q * a.dump_stride + ncand] = node;  // (index builder)
       }
       if (ncand < a.cand_cap) ++ncand;
@@ -1161,7 +1189,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
     if (MODE == kBase) {
       // ---- BANG_Base (A.1, A.2): seed, then { merge(previous) ; expand(parent) ; compute_parent2 } ----
       if (lane == 0) s.n_id[0] = a.medoid;
-      uint32_t n = expand<T, MODE, CS>(a, s, bloom, vb, my_nb, 1u, st, pf);
+      uint32_t n = expand<T, MODE, CS, PH>(a, s, bloom, vb, my_nb, 1u, st, pf);
       if (lane == 0) insert_medoid(a, bloom, vb);
       Best b = scan_neighbours(s, n, a.medoid, true, 0.0f);
       bool have = b.id != kNone;  // compute_parent1 (:1464-1521): closest seeded neighbour, medoid excluded
@@ -1170,7 +1198,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       uint32_t pend_n = n, pend_nb = min(n, a.L), pend_below = 0, scan_from = 0;
       float pend_maxd = 0.0f;
       while (have || pend_n > 0) {
-        if (have) my_nb = fetch_adj(a, parent, pol_stream, lane);  // in flight during the merge
+        if (have) my_nb = fetch_adj<PH>(a, parent, pol_stream, lane);  // in flight during the merge
         pf.tick(PT_DECIDE);
         if (pend_n > 0 && pend_nb > 0) {          // sort + merge of the previous neighbours (:726,:738), mark (:1711-1714)
           ws = merge_worklist(a, s, pend_n, pend_nb, pend_below, pend_maxd, ws, iter == 1, mark, &pos0);
@@ -1183,7 +1211,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         pf.tick(PT_UNVIS);
         pf.count(PT_HOPS);
         n = 0;
-        if (have) n = expand<T, MODE, CS>(a, s, bloom, vb, my_nb, 0u, st, pf);
+        if (have) n = expand<T, MODE, CS, PH>(a, s, bloom, vb, my_nb, 0u, st, pf);
         ++iter;
         // compute_parent2 (:1403-1458)
         const float maxd = ws > 0 ? w_dist(s, ws - 1) : 0.0f;
@@ -1207,7 +1235,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       }
       write_stats(a, s, q, st);
       pf.tick(PT_DECIDE);
-      rerank_and_write<T>(a, s, q, ncand);
+      rerank_and_write<T, PH>(a, s, q, ncand);
       pf.tick(PT_RERANK);
     } else {
       // ---- BANG_Inmemory / BANG_Exactdistance (A.2', A.2''): { expand(parent) ; merge ; first unvisited } ----
@@ -1217,7 +1245,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
       for (;;) {
         const bool first = iter == 1;
         if (first && lane == 0) s.n_id[0] = a.medoid;
-        const uint32_t n = expand<T, MODE, CS>(a, s, bloom, vb, my_nb, first ? 1u : 0u, st, pf);
+        const uint32_t n = expand<T, MODE, CS, PH>(a, s, bloom, vb, my_nb, first ? 1u : 0u, st, pf);
         if (first && lane == 0) insert_medoid(a, bloom, vb);
         // Exactdistance: a hop whose neighbours are all filtered out ends the query — what the reference's fused
         // kernel does when built for sm_100a (it scans the worklist up to a size it only sets when there are new
@@ -1249,7 +1277,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
         if (!from_new) { if (lane == 0) s.w[fu].y = parent | kVisitedBit; scan_from = fu + 1; }
         log_parent(parent);  // thread 0, Inmemory parANN.cu:1399-1418
         const bool capped = iter == a.max_iter - 1;
-        if (!capped) my_nb = fetch_adj(a, parent, pol_stream, lane);  // in flight during the merge
+        if (!capped) my_nb = fetch_adj<PH>(a, parent, pol_stream, lane);  // in flight during the merge
         pf.tick(PT_DECIDE);
         if (nb > 0) {
           ws = merge_worklist(a, s, n, nb, b.below, maxd, ws, first, from_new ? parent : kNone, &pos0);
@@ -1272,7 +1300,7 @@ __global__ void __launch_bounds__(WPC * 32, (MODE == kExact) ? 2 : 1) bang_searc
           a.out_dists[(size_t)q * a.k + r] = r < ws ? w_dist(s, r) : 3.402823466e+38f;
         }
       } else {
-        rerank_and_write<T>(a, s, q, ncand);
+        rerank_and_write<T, PH>(a, s, q, ncand);
         pf.tick(PT_RERANK);
       }
     }

@@ -475,7 +475,9 @@ def run_b200(args):
                    "parallelism": f"index replicated on {world} GPU(s), " + (f"one batch of {wl['q']} queries split over the GPUs" if strong
                                                                               else f"one batch of {wl['q']} queries per GPU") + ", no collective",
                    "l2": "256 MiB buffer written between timed iterations; index (rows+codes) larger than L2",
-                   "index_in_hbm_mib": int(info.device_bytes) >> 20, "kernel_source_hash": kernel_source_hash(), "builder": args.builder},
+                   "index_in_hbm_mib": int(info.device_bytes) >> 20, "row_bytes": int(info.row_stride),
+                   "rows": "64 neighbour ids + their precomputed visited-filter slots (512 B) + vector" if info.slot_block else "64 neighbour ids + vector",
+                   "kernel_source_hash": kernel_source_hash(), "builder": args.builder},
         "e2e": {"value": p90["e2e_qps"], "unit": "QPS", "ms_per_step": p90["e2e_ms"],
                 "h2d_bytes_per_step": int(Qtot * wl["d"] * esize(wl)), "d2h_bytes_per_step": int(Qtot * K * 12)},
         "at_recall_95": {"L": p95["L"], "recall_at_10": round(p95["recall"], 2), "value": p95["qps"], "ms_per_step": p95["ms"],
