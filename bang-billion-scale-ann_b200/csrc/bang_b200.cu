@@ -351,27 +351,21 @@ static int rows_check_end(bang_b200_ctx* c) {
   return BANG_OK;
 }
 
-// Row geometry.  PQ modes with 32 uniform chunks (the CS = 4 kernels) store, next to the 64 neighbour ids, the two
-// visited-filter slots of every neighbour (512 bytes per row) when the device has room for it: the kernel then reads
-// them with the adjacency instead of evaluating two 64-bit hashes + modulus per neighbour (13 % of a hop's
-// instructions).  BANG_B200_PREHASH=0 / 1 forces the choice; the default is on for an unsharded index whose enlarged
-// rows leave 8 GB of the device free (ranks of a sharded index would all have to take the same decision, and 10^9
-// points do not have the room anyway).  Call after the PQ tables are uploaded (chunk4) and the codes allocated.
+// Row geometry.  PQ modes with 32 uniform chunks (the CS = 4 kernels) can store, next to the 64 neighbour ids, the two
+// visited-filter slots of every neighbour (512 bytes per row): the kernel then reads them with the adjacency instead of
+// evaluating two 64-bit hashes + modulus per neighbour (12 % of a hop's instructions).  Opt-in, BANG_B200_PREHASH=1:
+// measured on one B200 it buys 2-4 % of time for twice the DRAM bytes and 1.8-2.3 x the row memory, because the hash
+// arithmetic mostly fills slots in which the warp would otherwise wait for memory (profiles/r2_hop_diet.md).  Call after
+// the PQ tables are uploaded (chunk4).
 static void set_row_geometry(bang_b200_ctx* c) {
   c->vec_bytes = c->D * (uint32_t)elem_size(c->dtype);
   c->vec_units = (c->vec_bytes + 15) / 16;
   c->rows_local = (c->N + c->n_shards - 1 - c->shard) / c->n_shards;
   const uint32_t plain = (uint32_t)align_up(kAdjBytes + (size_t)c->vec_units * 16, 32);
   const uint32_t wide = (uint32_t)align_up(kAdjBytes + kSlotBytes + (size_t)c->vec_units * 16, 32);
-  bool want = c->mode != BANG_MODE_EXACTDISTANCE && c->chunk4 != 0;
-  if (want) {
-    const char* e = getenv("BANG_B200_PREHASH");
-    if (e) want = atoi(e) != 0;
-    else {
-      size_t free_b = 0, total_b = 0;
-      want = c->n_shards == 1 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (size_t)c->rows_local * wide + (8ull << 30) <= free_b;
-    }
-  }
+  bool want = false;
+  if (c->mode != BANG_MODE_EXACTDISTANCE && c->chunk4 != 0)
+    if (const char* e = getenv("BANG_B200_PREHASH")) want = atoi(e) != 0;
   c->prehash = want;
   c->row_stride = want ? wide : plain;
 }

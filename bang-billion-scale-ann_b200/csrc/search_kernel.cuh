@@ -3,7 +3,7 @@
 // One warp owns one query at a time and walks the whole greedy search for it without leaving the SM:
 // { adjacency fetch, visited filter (stage 4a), PQ/exact distances (stages 1+3, the table entries are
 // evaluated on demand), parent selection (stage 2), (dist,id) sort + worklist merge (stage 4b) }* -> exact
-// re-rank + top-k (stage 5).  CTAs (up to 16 query warps + one pivot table) are persistent: the grid is sized
+// re-rank + top-k (stage 5).  CTAs (up to 32 query warps + one pivot table, 24 by default) are persistent: the grid is sized
 // to the number of resident CTAs and every warp pulls query indices from a global counter.  What the reference
 // does with ~5 kernel launches, 2 memsets, up to 5 PCIe copies and 3 stream syncs per hop
 // (bang_search.cu:701-958) is one launch here; the worklist, candidate log and neighbour lists never leave
@@ -16,19 +16,22 @@
 // residency at 6.  A table entry is a pure function of (query, chunk, code): tbl[c][k] = the fmaf chain
 // over the chunk's dimensions.  Evaluating that same chain on demand from ONE pivot table shared by all
 // the warps of the CTA (128 KB of shared memory at D = 128) gives bit-identical distances and leaves
-// ~4 KB of private state per query, i.e. 16-20 resident queries per SM.  CTA barriers are used once (to
-// publish the pivot table); afterwards every warp runs on its own with __syncwarp and redux.sync.
+// ~2.5 KB of private state per query (D = 128, L = 176), i.e. 24 resident queries per SM below the 196 KB
+// shared-memory step.  CTA barriers are used once (to publish the pivot table); afterwards every warp runs on
+// its own with __syncwarp and redux.sync.
 // Per hop:
 //   * the adjacency row (256 B) was requested at the end of the previous hop, one 8-byte load per lane;
-//   * visited filter with snapshot semantics: 4 filter blocks (16 B each) per lane in one L2 round trip;
-//     insertion = one atomic on the block's count (hands out the byte position) + a byte store after the
-//     distance phase, so nothing waits on the atomic's round trip;
+//   * visited filter with snapshot semantics: 4 filter blocks (8 B each) per lane in one L2 round trip, addressed as
+//     32-bit offsets from one kernel parameter; insertion = one atomic on the block's count (hands out the byte
+//     position) + a byte store after the distance phase, so nothing waits on the atomic's round trip; the rare
+//     overflowing blocks sit behind one warp vote;
 //   * 8 lanes per accepted candidate for the distance, 16 candidates' code loads in flight;
 //   * the next node to expand is decided from the unsorted distances BEFORE the sort/merge (it is the
 //     smaller of the best admitted new candidate and the first unvisited worklist entry — exactly what
 //     the merge would produce) and its adjacency row is requested at once, so the merge overlaps the
 //     DRAM latency of the next hop;
 //   * in-place merge, 32 entries at a time from the tail, only from the first insertion point on.
+// Where a hop's ~930 warp instructions and its stalls go: profiles/r2_hop_diet.md.
 //
 // Semantics are the reference's with the deterministic choices documented in
 // oracle/bang_oracle.c; the oracle is bit-exact with this kernel (ORDER_GPU).
@@ -759,7 +762,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
   __syncwarp();
   pf.tick(PT_COMPACT);
   // The reserved filter bytes are stored after the distance computations of the hop: the atomics that hand out the
-  // byte positions have long returned by then, so nothing waits for their round trip.
+  // byte positions have long returned by then, so nothing waits for their round trip (storing them while the first
+  // code words travel instead measured 8 % slower on the C2 shape, profiles/r2r_reorder_variants_ab.log).
   const uint32_t t = lane & 7, g = lane >> 3;  // 4 candidates per pass
   if (MODE == kExact) {
     for (uint32_t k0 = 0; k0 < n; k0 += 8) {  // two rows in flight per lane group
@@ -794,8 +798,8 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
 #endif
       const uint32_t kend = min(n, k0 + 16);
 #pragma unroll 1
-      for (uint32_t kb = k0; kb < kend; kb += 4) {  // (not unrolled: the kernel's hot loop has to stay inside the instruction cache)
-        const float sum = tree8(adc4_word(pa, w0, q0, q1, q2, q3));
+      for (uint32_t kb = k0; kb < kend; kb += 4) {  // (not unrolled: the kernel's hot loop has to stay inside the instruction cache; two
+        const float sum = tree8(adc4_word(pa, w0, q0, q1, q2, q3));  // candidates per pass measured +-1 %, profiles/r2r_reorder_variants_ab.log)
         if (t == 0 && kb + g < n) s.n_d[kb + g] = sum;
         w0 = w1; w1 = w2; w2 = w3;
       }
@@ -1350,7 +1354,8 @@ inline LaunchGeom launch_geometry(int mode, uint32_t piv_row, uint32_t n_chunks,
   // Shared memory and L1 share 256 KB per SM and the split moves in steps (... 164, 196, 228 KB of shared memory, 1 KB per
   // CTA reserved by the system).  The gathers of the traversal are scattered 8..32-byte loads whose lines in flight live
   // in L1: crossing from the 196 KB step (60 KB of L1) to the 228 KB step (28 KB) costs 15 % on the C2 shape at the same
-  // number of warps (profiles/r2_l1_carveout.md), so the PQ modes give up a few resident queries to stay below the step.
+  // number of warps (C2 at 24 warps: 4.65 -> 3.85 ms when the state was cut to fit, profiles/r2_hop_diet.md), so the PQ modes give up a few
+  // resident queries to stay below the step.
   if (keep_l1 && mode != kExact) {
     const size_t step = (size_t)196 * 1024 - 1024;
     if (shared + (size_t)w * per > step && shared + 16 * per <= step) w = (int)((step - shared) / per);

@@ -20,7 +20,7 @@ runs `bench.py --prepare` in a child process and then only reads the files.
 
 JSON line (one, from rank 0): `value` = whole-job QPS at recall@10 >= 0.90 with queries already resident in HBM
 (CUDA events on the launching stream, max over ranks); `e2e` = the same through the host-facing bang_query call
-(pinned host query buffer in, host ids/dists out); `at_recall_95` repeats both at the >= 0.95 operating point;
+(pinned host query buffer in, pinned host ids/dists buffers out); `at_recall_95` repeats both at the >= 0.95 operating point;
 `strong_scaling` = the same 10 000 queries split over the ranks.
 """
 from __future__ import annotations
@@ -295,13 +295,16 @@ def time_config(search, queries_np, L, steps, warmup, device, world):
         search.bang_init(Q)
         search.bang_query(q_host)
     e2e_ms = []
+    # (the caller's result buffers are pinned as well: bang_query copies straight into them)
+    ids_host = torch.empty((Q, K), dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    dists_host = torch.empty((Q, K), dtype=torch.float32).pin_memory().numpy()
     barrier()
     for s in range(steps):
         flush.zero_()
         torch.cuda.synchronize(device)
         search.bang_init(Q)
         t0 = time.perf_counter()
-        ids_host, _ = search.bang_query(q_host)
+        search.bang_query(q_host, None, ids_host, dists_host)
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
     tm = search.last_timing()
     assert np.array_equal(ids_host, ids_dev), "device-resident and host paths disagree"

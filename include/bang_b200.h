@@ -126,7 +126,7 @@ typedef struct {
   int32_t dtype, mode;
   uint64_t device_bytes;  /* HBM held by the index on this device */
   uint32_t row_stride;    /* bytes per graph row in HBM: 64 neighbour ids [+ 512 B of precomputed visited-filter slots] + vector */
-  uint32_t slot_block;    /* 1: the rows carry the slot block (PQ modes with 32 uniform chunks when memory allows; BANG_B200_PREHASH=0/1) */
+  uint32_t slot_block;    /* 1: the rows carry the slot block (opt-in for PQ modes with 32 uniform chunks: BANG_B200_PREHASH=1) */
 } bang_b200_info_t;
 int bang_b200_info(bang_handle_t h, bang_b200_info_t* out);
 
