@@ -167,7 +167,8 @@ struct bang_b200_ctx {
   uint64_t device_bytes = 0;
   unsigned long long* d_bad = nullptr;  // row validation counters: degree > R, id >= N, duplicate id (see validate_row)
   bool piv_global = false;              // the pivot table does not fit in shared memory: read it from global/L2
-  bool code_prefetch = true;            // speculative L2 prefetch of every neighbour's PQ code row (BANG_B200_CODE_PREFETCH)
+  bool code_prefetch = false;           // speculative L2 prefetch of every neighbour's PQ code row (BANG_B200_CODE_PREFETCH=1): no longer
+                                        // pays (same time, +47 % DRAM bytes at 10^7 points, profiles/r2u_dram_bytes_prefetch_l2fetch.log)
   bool prehash = false;                 // rows carry their neighbours' visited-filter slots (kSlotBytes; decided at load, see set_row_geometry)
   // params
   int k = 0, L = 0, distfn = BANG_DIST_L2, dists_layout = BANG_DISTS_RANK_MAJOR;

@@ -241,7 +241,9 @@ __device__ __forceinline__ uint32_t ld_nc_u32(const void* p, uint64_t pol) {
 }
 // Speculative L2 prefetch of one 32-byte sector: issued for the PQ codes of ALL neighbours of the expanded node
 // as soon as their ids arrive, i.e. in parallel with the visited-filter round trip.  The real code loads (only
-// for the candidates that pass the filter) then hit L2 instead of paying a second dependent DRAM access.
+// for the candidates that pass the filter) then hit L2 instead of paying a second dependent DRAM access.  Off by
+// default since the instruction diet: the wait it covered is hidden by the other warps now, and it cost 47 % more
+// DRAM bytes at 10^7 points (SearchArgs::code_prefetch, profiles/r2u_dram_bytes_prefetch_l2fetch.log).
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // ---- sparse visited filter (see kVisBlocks) -------------------------------------------------------
