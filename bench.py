@@ -725,7 +725,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--prepare", action="store_true", help="build + cache the index files and operating points, then exit")
-    ap.add_argument("--n", type=int, default=0, help="override the number of base points (parity/debug runs only)")
+    ap.add_argument("--n", "--points", dest="n", type=int, default=0,
+                    help="override the number of base points (parity/debug runs only; under torchrun spell it --points: its own parser trips over --n)")
     ap.add_argument("--q", type=int, default=0)
     ap.add_argument("--L", type=int, default=0, help="fix the worklist length instead of using the cached sweep")
     ap.add_argument("--L95", type=int, default=0)
