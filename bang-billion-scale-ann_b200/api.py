@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "bang_b200_load_device_begin", "bang_b200_load_device_rows",
     "bang_b200_load_device_codes", "bang_b200_load_device_codes_at", "bang_b200_load_device_end", "bang_b200_set_searchparams", "bang_b200_alloc",
     "bang_b200_init", "bang_b200_query", "bang_b200_free", "bang_b200_unload", "bang_b200_set_dists_layout",
-    "bang_b200_query_device", "bang_b200_pq_table", "bang_b200_info", "bang_b200_last_stats",
+    "bang_b200_query_device", "bang_b200_pq_table", "bang_b200_info", "bang_b200_filter_slots", "bang_b200_last_stats",
     "bang_b200_last_timing", "bang_b200_last_error", "bang_b200_bruteforce_gt", "bang_b200_pq_train", "bang_b200_pq_encode",
     "bang_b200_prep_last_error", "bang_load_c", "bang_set_searchparams_c", "bang_query_c",
     "bang_unload_c",
@@ -99,6 +99,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         "bang_b200_query_device": (ci, [vp, vp, ci, vp, vp, vp]),
         "bang_b200_pq_table": (ci, [vp, vp, ci, vp]),
         "bang_b200_info": (ci, [vp, ctypes.POINTER(Info)]),
+        "bang_b200_filter_slots": (None, [ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32 * 2), ctypes.POINTER(ctypes.c_uint32 * 2)]),
         "bang_b200_last_stats": (ci, [vp, vp, vp, vp]),
         "bang_b200_last_timing": (ci, [vp, ctypes.POINTER(Timing)]),
         "bang_b200_last_error": (ctypes.c_char_p, []),
@@ -114,6 +115,14 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     if path == _build.LIB_CUDA:
         _lib = lib
     return lib
+
+
+def filter_slots(point_id: int):
+    """(positions, slot words) of a point id in the visited filter — host arithmetic of the library (bang_b200_filter_slots)."""
+    lib = load_library()
+    pos, words = (ctypes.c_uint32 * 2)(), (ctypes.c_uint32 * 2)()
+    lib.bang_b200_filter_slots(ctypes.c_uint32(point_id), ctypes.byref(pos), ctypes.byref(words))
+    return (pos[0], pos[1]), (words[0], words[1])
 
 
 class BANGSearch:

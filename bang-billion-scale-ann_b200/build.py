@@ -58,7 +58,7 @@ def _srcs(d: str, exts=(".cu", ".cuh", ".cpp", ".h", ".c")) -> list[str]:
     return out
 
 
-CUDA_SOURCES = ["bang_b200.cu", "builder.cu", "prep_kernels.cu", "search_inst_u8.cu", "search_inst_i8.cu", "search_inst_f32.cu"]
+CUDA_SOURCES = ["bang_b200.cu", "builder.cu", "prep_kernels.cu", "filter_slots.cu", "search_inst_u8.cu", "search_inst_i8.cu", "search_inst_f32.cu"]
 HOST_SOURCES = ["loader.cpp", "bang_shim.cpp", "shard_mem.cpp"]
 
 

@@ -130,6 +130,12 @@ typedef struct {
 } bang_b200_info_t;
 int bang_b200_info(bang_handle_t h, bang_b200_info_t* out);
 
+/* The two visited-filter slots of a point id, computed on the host exactly as the load kernels write them into the rows'
+ * slot block and as the kernels evaluate them per hop: pos[i] = hashFn1_d / hashFn2_d (bang_search.cu:1168-1189) of the
+ * id, in [0, 399887); words[i] = (pos / 255 * 8) | (pos % 255) << 24, i.e. the byte offset of the slot's 8-byte block in
+ * a query's sparse filter and the slot's offset inside the block.  No device is touched. */
+void bang_b200_filter_slots(uint32_t id, uint32_t pos[2], uint32_t words[2]);
+
 /* Per-query counters of the last query call (host arrays of length Q, any may be NULL):
  * hops = expanded nodes incl. medoid, sum_deg = sum of their degrees, n_cand = candidates that passed
  * the visited filter.  These feed the roofline's algorithmic-bytes figure. */

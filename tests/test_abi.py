@@ -60,3 +60,22 @@ def test_reference_driver_links_against_this_library():
     import subprocess
     out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
     assert "libbang_b200.so" in out and "libbang.so" not in out
+
+
+def test_filter_slots_match_the_reference_hashes():
+    """The load-time form of the visited-filter slots (rows with the slot block) and the per-hop form in the kernel share one
+    host/device function pair; its host side must give the reference's hashFn1_d / hashFn2_d (bang_search.cu:1168-1189, as
+    restated in oracle/bang_oracle.c) for any id, and the documented word format.  Host arithmetic only: no device needed."""
+    import numpy as np
+    import oracle as O
+    from bang_b200 import api
+    rng = np.random.default_rng(5)
+    ids = [0, 1, 254, 255, 256, 65535, 65536, 399886, 399887, 2**24 - 1, 2**24, 2**31 - 1, 2**31, 0xFFFFFFFE, 0xFFFFFFFF]
+    ids += [int(x) for x in rng.integers(0, 2**32, size=2000, dtype=np.uint64)]
+    for i in ids:
+        pos, words = api.filter_slots(i)
+        assert pos == (O.hash1(i), O.hash2(i)), i
+        for p, w in zip(pos, words):
+            assert p < 399887
+            assert w == ((p // 255 * 8) | ((p % 255) << 24))
+            assert (w & 0xFFFF) < 1569 * 8 and (w >> 24) < 255 and (w & 0x00FF0007) == 0
