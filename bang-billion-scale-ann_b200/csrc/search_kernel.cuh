@@ -784,16 +784,25 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
     const float4 q0 = lds_f4_off<0>(qa), q1 = lds_f4_off<128>(qa), q2 = lds_f4_off<256>(qa), q3 = lds_f4_off<384>(qa);
     const uint8_t* cbase;  // codes + 4 t (32 chunks: 32-byte code rows); opaque, so that it is formed once per hop and not once per load
     asm volatile("add.u64 %0, %1, %2;" : "=l"(cbase) : "l"(a.codes), "l"((unsigned long long)(4u * t)));
-    for (uint32_t k0 = 0; k0 < n; k0 += 16) {
-      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    // the code words of the candidates k0 + g, + 4, + 8, + 12 of this lane group (beyond n: 0; the ids read there are stale
+    // entries of the list block, never used)
+    auto load_words = [&](uint32_t k0, uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3) {
       const uint32_t kg = k0 + g;
-      // (the four ids are read without a guard: beyond n they are stale entries of the list block, never used)
       const uint32_t* np = s.n_id + kg;
       const uint32_t i0 = np[0], i1 = np[4], i2 = np[8], i3 = np[12];
-      if (kg < n) w0 = ld_nc_u32(code_row(cbase, i0), s.pol_stream);
-      if (kg + 4 < n) w1 = ld_nc_u32(code_row(cbase, i1), s.pol_stream);
-      if (kg + 8 < n) w2 = ld_nc_u32(code_row(cbase, i2), s.pol_stream);
-      if (kg + 12 < n) w3 = ld_nc_u32(code_row(cbase, i3), s.pol_stream);
+      x0 = x1 = x2 = x3 = 0;
+      if (kg < n) x0 = ld_nc_u32(code_row(cbase, i0), s.pol_stream);
+      if (kg + 4 < n) x1 = ld_nc_u32(code_row(cbase, i1), s.pol_stream);
+      if (kg + 8 < n) x2 = ld_nc_u32(code_row(cbase, i2), s.pol_stream);
+      if (kg + 12 < n) x3 = ld_nc_u32(code_row(cbase, i3), s.pol_stream);
+    };
+    uint32_t w0, w1, w2, w3;
+    load_words(0, w0, w1, w2, w3);
+    for (uint32_t k0 = 0; k0 < n; k0 += 16) {
+      // the next 16 candidates' words are requested before this batch is evaluated (lists longer than 16 are the rule on the
+      // DEEP shape at small L, where the wait for the second batch was 18 % of the stall samples: profiles/r2_hop_diet.md §7)
+      uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+      if (k0 + 16 < n) load_words(k0 + 16, x0, x1, x2, x3);
 #ifdef BANG_PHASE_TIMERS
       if (__any_sync(kFull, (w0 ^ w1 ^ w2 ^ w3) == 0x12345678u)) printf("");
       pf.tick(PT_CODEWAIT);
@@ -805,6 +814,7 @@ __device__ __forceinline__ uint32_t expand(const SearchArgs& a, const QState& s,
         if (t == 0 && kb + g < n) s.n_d[kb + g] = sum;
         w0 = w1; w1 = w2; w2 = w3;
       }
+      w0 = x0; w1 = x1; w2 = x2; w3 = x3;
     }
   } else {
     // any chunk layout (uneven chunks, m != 32: the reference's SIFT1B build has 74, SIFT10K 128): 32 chunks per group
